@@ -1,0 +1,116 @@
+/* sctl_cuda.h -- C ABI of the B200-native (sm_100a) dense kernel-summation module.
+ *
+ * Drop-in boundary for SCTL's GenericKernel<uKernel>::Eval / KernelMatrix (reference paths are relative to
+ * /root/reference/include/sctl/):
+ *
+ *   sctl_cuda_eval            replaces the body of GenericKernel<uK>::Eval<Real,omp,digits>
+ *                             (generic-kernel.txx:102-211) and is what the runtime-digits trampoline
+ *                             Eval<Real,omp>(..., Integer digits, ConstIterator<char> self)
+ *                             (generic-kernel.hpp:99, generic-kernel.txx:72-100) ends up calling.
+ *   sctl_cuda_kernel_matrix   replaces GenericKernel<uK>::KernelMatrix<Real,omp,digits>
+ *                             (generic-kernel.txx:213-329).
+ *   sctl_cuda_kernel_info     mirrors CoordDim/NormalDim/SrcDim/TrgDim (generic-kernel.txx:48-62),
+ *                             uKernel::FLOPS() and uKerScaleFactor<Real>() (kernel_functions.hpp:37-42, ...).
+ *
+ * All arrays are the reference's AoS Vector<Real> layouts (generic-kernel.txx:141,145-147,154):
+ *   r_src[Ns*3], n_src[Ns*ND] (may be NULL when ND == 0), v_src[Ns*K0], r_trg[Nt*3], v_trg[Nt*K1],
+ *   M[(Ns*K0) x (Nt*K1)] row-major with leading dimension ldM;  Real = double (real_bytes 8) or float (4).
+ * (K0, K1, ND) per kernel id: FxU (1,1,0)  DxU (1,1,3)  FxdU (1,3,0)  Stokes FxU (3,3,0)  Stokes DxU (3,3,3).
+ *
+ * Semantics kept from the reference:
+ *   - Eval ACCUMULATES: v_trg += scale * sum_s K(x_t - x_s, n_s) f_s  (generic-kernel.txx:204-208).  The
+ *     "wrong size => ReInit + SetZero" rule (:129-132) is applied by the C++ wrapper before the call.
+ *   - KernelMatrix OVERWRITES M (:268,306).
+ *   - pairs with r^2 == 0 contribute exactly 0 (approx_rsqrt(r2, r2 > 0), kernel_functions.hpp:45).
+ *   - digits in [-1, 15] selects the accuracy of the reciprocal square root exactly like
+ *     approx_rsqrt<digits> (vec.txx:375-382): the result is accurate to at least `digits` decimal digits;
+ *     -1 = working precision of Real.  Values >= 16 are treated as -1 (generic-kernel.txx:97).
+ *   - inputs are never modified; no pointer is retained after return.
+ * Errors: the reference aborts through SCTL_ASSERT (common.hpp:98-105).  Here every entry returns 0 on success
+ * and nonzero on failure, with a thread-local message in sctl_cuda_last_error(); the C++ wrapper turns that
+ * into SCTL_ERROR.  There is NO CPU fallback: without a usable CUDA device every compute entry fails.
+ * Threading: every entry may be called concurrently from many host threads (the reference calls
+ * KernelMatrix<Real,false> inside an OpenMP parallel loop, boundary_integral.txx:1169-1211); each host thread
+ * gets its own stream.
+ */
+#ifndef SCTL_CUDA_H_
+#define SCTL_CUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum sctl_cuda_kernel_id {
+  SCTL_CUDA_LAPLACE3D_FXU = 0,  /* sctl::Laplace3D_FxU   kernel_functions.hpp:32-59   */
+  SCTL_CUDA_LAPLACE3D_DXU = 1,  /* sctl::Laplace3D_DxU   kernel_functions.hpp:61-79   */
+  SCTL_CUDA_LAPLACE3D_FXDU = 2, /* sctl::Laplace3D_FxdU  kernel_functions.hpp:81-123  */
+  SCTL_CUDA_STOKES3D_FXU = 3,   /* sctl::Stokes3D_FxU    kernel_functions.hpp:125-178 */
+  SCTL_CUDA_STOKES3D_DXU = 4,   /* sctl::Stokes3D_DxU    kernel_functions.hpp:180-218 */
+  SCTL_CUDA_NUM_KERNELS = 5
+};
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+
+/* Number of CUDA devices visible to this process (0 when there is no driver / device). */
+int sctl_cuda_device_count(void);
+
+/* Select how many GPUs the host-pointer entries shard over (0 = all visible).  Optional: the first compute
+ * call initialises one GPU (the calling thread's current device).  n_gpus > 1 creates one NCCL communicator
+ * over devices 0..n_gpus-1 of this process (sources are replicated with ncclBroadcast over NVLink, targets
+ * are sharded by contiguous ranges -- the block rule of ParticleFMM::EvalDirect, fmm-wrapper.txx:565-569). */
+int sctl_cuda_init(int n_gpus);
+int sctl_cuda_finalize(void);
+/* GPUs the host-pointer entries currently shard over (>= 1 once initialised, 0 before). */
+int sctl_cuda_num_gpus(void);
+
+/* Thread-local description of the last failure on the calling thread ("" if none). */
+const char* sctl_cuda_last_error(void);
+
+/* ---- kernel metadata ------------------------------------------------------------------------ */
+
+/* Any out pointer may be NULL.  name: "Laplace3D-FxU" ... (uKernel::Name()).  scale: uKerScaleFactor<double>().
+ * f_alg: algorithmic flop per pair used for the roofline. */
+int sctl_cuda_kernel_info(int kernel_id, int* k0, int* k1, int* nd, int* flops, int* f_alg, double* scale, const char** name);
+
+/* ---- the hot path: host pointers (the drop-in entries) -------------------------------------- */
+
+int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
+                   const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg,
+                   const void* ctx, int64_t ctx_bytes /* uKernel context (GetCtxPtr); unused by the five kernels */);
+
+int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
+                            const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM);
+
+/* ---- the hot path: device pointers on the current device, enqueued on `stream` -------------- */
+/* (cudaStream_t passed as void*; NULL = the legacy default stream.)  Asynchronous: returns after enqueueing.
+ * Pointers need no particular alignment.  Scratch comes from the stream-ordered pool (cudaMallocAsync). */
+
+int sctl_cuda_eval_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
+                          const void* d_r_src, const void* d_n_src, const void* d_v_src, const void* d_r_trg, void* d_v_trg,
+                          void* stream);
+
+int sctl_cuda_kernel_matrix_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
+                                   const void* d_r_src, const void* d_n_src, const void* d_r_trg, void* d_M, int64_t ldM,
+                                   void* stream);
+
+/* ---- measurement and test hooks ------------------------------------------------------------- */
+
+/* Device-side twin of approx_rsqrt<digits>(x, x > 0) on n device values (contract test, vec-test.hpp:431-465). */
+int sctl_cuda_rsqrt_device(int real_bytes, int digits, int64_t n, const void* d_x, void* d_y, void* stream);
+
+/* Timings (ms, CUDA events on the call's stream) of the calling thread's last host-pointer call. */
+int sctl_cuda_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
+
+/* Launch geometry the last device-level Eval of the calling thread used (any pointer may be NULL). */
+int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes, int* ctas_per_sm, int* n_launches, double* wave_eff);
+
+/* FMA-throughput micro-benchmark of the current device: dependent-free DFMA (real_bytes 8) or FFMA (4)
+ * chains for about `ms` milliseconds; returns achieved TFLOP/s (FMA = 2 flop) -- the roofline denominator. */
+int sctl_cuda_fma_peak(int real_bytes, double ms, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCTL_CUDA_H_ */

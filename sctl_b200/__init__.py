@@ -1,0 +1,273 @@
+"""sctl_b200 -- B200-native dense kernel summation behind SCTL's GenericKernel API.
+
+Python host-side mirror of ``sctl::GenericKernel<uKernel>`` (reference: include/sctl/generic-kernel.hpp:48-136)
+for the five in-scope micro-kernels (include/sctl/kernel_functions.hpp:32-218).  Everything computes through the
+C ABI in ``include/sctl_cuda.h`` (``libsctl_cuda.so``, hand-written sm_100a CUDA); there is no CPU fallback and
+importing the compute entries without the built library raises.
+
+    import sctl_b200 as sb
+    K = sb.Stokes3D_FxU
+    v = K.Eval(None, r_trg, r_src, None, v_src)         # numpy in / numpy out (host path, H2D + kernel + D2H)
+    sb.eval_device("Stokes3D_FxU", d_r_src, None, d_v_src, d_r_trg, d_v_trg)   # torch CUDA tensors, in place
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsctl_cuda.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sctl_cuda.h")
+
+KERNEL_IDS = {"Laplace3D_FxU": 0, "Laplace3D_DxU": 1, "Laplace3D_FxdU": 2, "Stokes3D_FxU": 3, "Stokes3D_DxU": 4}
+
+_lib = None
+
+
+class SctlCudaError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load libsctl_cuda.so (built in-tree by ``__graft_entry__.build()`` / ``make -C sctl_b200/csrc``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SctlCudaError("%s is missing: build it with `make -C sctl_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    i, i64, vp, dp = C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_double)
+    ip = C.POINTER(C.c_int)
+    L.sctl_cuda_device_count.restype = i
+    L.sctl_cuda_init.argtypes = [i]
+    L.sctl_cuda_num_gpus.restype = i
+    L.sctl_cuda_last_error.restype = C.c_char_p
+    L.sctl_cuda_kernel_info.argtypes = [i, ip, ip, ip, ip, ip, dp, C.POINTER(C.c_char_p)]
+    L.sctl_cuda_eval.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, vp, vp, i64]
+    L.sctl_cuda_kernel_matrix.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, i64]
+    L.sctl_cuda_eval_device.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, vp, vp]
+    L.sctl_cuda_kernel_matrix_device.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, i64, vp]
+    L.sctl_cuda_rsqrt_device.argtypes = [i, i, i64, vp, vp, vp]
+    L.sctl_cuda_last_timing.argtypes = [dp, dp, dp]
+    L.sctl_cuda_last_plan.argtypes = [ip, ip, ip, ip, ip, ip, dp]
+    L.sctl_cuda_fma_peak.argtypes = [i, C.c_double, dp]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise SctlCudaError(load_library().sctl_cuda_last_error().decode() or "sctl_cuda call failed (rc=%d)" % rc)
+
+
+def _kid(kernel):
+    if isinstance(kernel, GenericKernel):
+        return kernel.kernel_id
+    if isinstance(kernel, str):
+        return KERNEL_IDS[kernel]
+    return int(kernel)
+
+
+def device_count():
+    return int(load_library().sctl_cuda_device_count())
+
+
+def init(n_gpus=0):
+    """sctl_cuda_init: shard host-pointer calls over ``n_gpus`` GPUs of this process (0 = all visible)."""
+    _check(load_library().sctl_cuda_init(int(n_gpus)))
+    return int(load_library().sctl_cuda_num_gpus())
+
+
+def finalize():
+    _check(load_library().sctl_cuda_finalize())
+
+
+def kernel_info(kernel):
+    L = load_library()
+    k0, k1, nd, fl, fa = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    sc, nm = C.c_double(), C.c_char_p()
+    _check(L.sctl_cuda_kernel_info(_kid(kernel), C.byref(k0), C.byref(k1), C.byref(nd), C.byref(fl), C.byref(fa), C.byref(sc), C.byref(nm)))
+    return dict(k0=k0.value, k1=k1.value, nd=nd.value, flops=fl.value, f_alg=fa.value, scale=sc.value, name=nm.value.decode())
+
+
+def last_timing():
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
+    load_library().sctl_cuda_last_timing(C.byref(a), C.byref(b), C.byref(c))
+    return dict(h2d_ms=a.value, kernel_ms=b.value, d2h_ms=c.value)
+
+
+def last_plan():
+    v = [C.c_int() for _ in range(6)]
+    w = C.c_double()
+    load_library().sctl_cuda_last_plan(*[C.byref(x) for x in v], C.byref(w))
+    keys = ["grid_x", "grid_y", "threads", "smem_bytes", "ctas_per_sm", "n_launches"]
+    out = {k: x.value for k, x in zip(keys, v)}
+    out["wave_eff"] = w.value
+    return out
+
+
+def fma_peak(real_bytes=8, ms=200.0):
+    """Measured FMA throughput (TFLOP/s) of the current device: the FP64/FP32 CUDA-core roofline denominator."""
+    t = C.c_double()
+    _check(load_library().sctl_cuda_fma_peak(int(real_bytes), float(ms), C.byref(t)))
+    return t.value
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def _dev_ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+def _real_bytes_of(t):
+    return 8 if "64" in str(t.dtype) else 4
+
+
+def eval_device(kernel, d_r_src, d_n_src, d_v_src, d_r_trg, d_v_trg, digits=-1, stream=None, Ns=None, Nt=None, real_bytes=None):
+    """sctl_cuda_eval_device on torch CUDA tensors (or raw device addresses): d_v_trg += K * d_v_src, asynchronous."""
+    L = load_library()
+    kid = _kid(kernel)
+    if Ns is None:
+        Ns = d_r_src.numel() // 3
+    if Nt is None:
+        Nt = d_r_trg.numel() // 3
+    if real_bytes is None:
+        real_bytes = _real_bytes_of(d_r_src)
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _check(L.sctl_cuda_eval_device(kid, real_bytes, int(digits), int(Ns), int(Nt), _dev_ptr(d_r_src), _dev_ptr(d_n_src), _dev_ptr(d_v_src),
+                                   _dev_ptr(d_r_trg), _dev_ptr(d_v_trg), C.c_void_p(stream)))
+
+
+def kernel_matrix_device(kernel, d_r_src, d_n_src, d_r_trg, d_M, digits=-1, stream=None, ldM=None):
+    L = load_library()
+    kid = _kid(kernel)
+    Ns, Nt = d_r_src.numel() // 3, d_r_trg.numel() // 3
+    info = kernel_info(kid)
+    if ldM is None:
+        ldM = Nt * info["k1"]
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _check(L.sctl_cuda_kernel_matrix_device(kid, _real_bytes_of(d_r_src), int(digits), Ns, Nt, _dev_ptr(d_r_src), _dev_ptr(d_n_src), _dev_ptr(d_r_trg),
+                                            _dev_ptr(d_M), int(ldM), C.c_void_p(stream)))
+
+
+def rsqrt_device(d_x, d_y, digits=-1, stream=None):
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream
+    _check(load_library().sctl_cuda_rsqrt_device(_real_bytes_of(d_x), int(digits), d_x.numel(), _dev_ptr(d_x), _dev_ptr(d_y), C.c_void_p(stream)))
+
+
+class GenericKernel:
+    """Host-side mirror of ``sctl::GenericKernel<uKernel>`` (generic-kernel.hpp:48-136) for one micro-kernel.
+
+    Static metadata (dims, name, FLOPS, scale factor) needs no GPU.  ``Eval`` / ``KernelMatrix`` take the
+    reference's AoS arrays (numpy, any shape that flattens to ``[N*dim]``) and go through the host-pointer C ABI.
+    """
+
+    # (KDIM0, KDIM1, N_DIM), FLOPS(), Name(): kernel_functions.hpp:33-42, 62-71, 82-91, 126-135, 181-190
+    _META = {
+        0: (1, 1, 0, 6, "Laplace3D-FxU"), 1: (1, 1, 3, 14, "Laplace3D-DxU"), 2: (1, 3, 0, 11, "Laplace3D-FxdU"),
+        3: (3, 3, 0, 23, "Stokes3D-FxU"), 4: (3, 3, 3, 26, "Stokes3D-DxU"),
+    }
+
+    def __init__(self, kernel):
+        self.kernel_id = KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
+        self._k0, self._k1, self._nd, self._flops, self._name = self._META[self.kernel_id]
+        self._ctx = None
+
+    def CoordDim(self):
+        return 3
+
+    def NormalDim(self):
+        return self._nd
+
+    def SrcDim(self):
+        return self._k0
+
+    def TrgDim(self):
+        return self._k1
+
+    def Name(self):
+        return self._name
+
+    def FLOPS(self):
+        return self._flops
+
+    def SetCtxPtr(self, ctx):
+        self._ctx = ctx
+
+    def GetCtxPtr(self):
+        return self._ctx
+
+    def uKerScaleFactor(self, dtype=np.float64):
+        pi = dtype(np.pi)
+        one = dtype(1)
+        return {0: one / (4 * pi), 1: one / (4 * pi), 2: -one / (4 * pi), 3: one / (8 * pi), 4: dtype(3) / (4 * pi)}[self.kernel_id]
+
+    def _arrays(self, r_trg, r_src, n_src, v_src, dtype, need_v=True):
+        r_trg = np.ascontiguousarray(r_trg, dtype=dtype).reshape(-1)
+        r_src = np.ascontiguousarray(r_src, dtype=dtype).reshape(-1)
+        Ns, Nt = r_src.size // 3, r_trg.size // 3
+        # SCTL_ASSERTs of generic-kernel.txx:125-128 (the reference aborts; here they raise)
+        if r_trg.size != Nt * 3:
+            raise SctlCudaError("r_trg.Dim() == Nt*DIM violated")
+        if r_src.size != Ns * 3:
+            raise SctlCudaError("r_src.Dim() == Ns*DIM violated")
+        if need_v:
+            v_src = np.ascontiguousarray(v_src, dtype=dtype).reshape(-1)
+            if v_src.size != Ns * self._k0:
+                raise SctlCudaError("v_src.Dim() == Ns*KDIM0 violated")
+        if self._nd:
+            n_src = np.ascontiguousarray(n_src if n_src is not None else [], dtype=dtype).reshape(-1)
+            if n_src.size != Ns * self._nd:
+                raise SctlCudaError("n_src.Dim() == Ns*N_DIM violated")
+        else:
+            n_src = None  # tolerated and ignored for single-layer kernels (:128)
+        return Ns, Nt, r_trg, r_src, n_src, v_src
+
+    def Eval(self, v_trg, r_trg, r_src, n_src, v_src, digits=-1, dtype=None):
+        """``Eval<Real,omp,digits>`` (generic-kernel.txx:102-211).  Returns v_trg: accumulated into (a copy-free view of)
+        the given array when it has Nt*K1 elements, else a fresh zero-initialised array (:129-132)."""
+        if dtype is None:
+            dtype = np.asarray(r_src).dtype.type if np.asarray(r_src).dtype in (np.float32, np.float64) else np.float64
+        Ns, Nt, r_trg, r_src, n_src, v_src = self._arrays(r_trg, r_src, n_src, v_src, dtype)
+        if v_trg is None or np.asarray(v_trg).size != Nt * self._k1:
+            out = np.zeros(Nt * self._k1, dtype=dtype)
+        else:
+            out = v_trg if (isinstance(v_trg, np.ndarray) and v_trg.dtype == dtype and v_trg.flags.c_contiguous) else np.ascontiguousarray(v_trg, dtype=dtype)
+        flat = out.reshape(-1)
+        if digits >= 16:
+            digits = -1  # generic-kernel.txx:97
+        _check(load_library().sctl_cuda_eval(self.kernel_id, flat.itemsize, int(digits), Ns, Nt, _np_ptr(r_src), _np_ptr(n_src), _np_ptr(v_src),
+                                             _np_ptr(r_trg), _np_ptr(flat), None, 0))
+        return out
+
+    def KernelMatrix(self, Xt, Xs, Xn, digits=-1, dtype=None, M=None):
+        """``KernelMatrix<Real,omp,digits>`` (generic-kernel.txx:213-329): (Ns*K0) x (Nt*K1), overwritten."""
+        if dtype is None:
+            dtype = np.asarray(Xs).dtype.type if np.asarray(Xs).dtype in (np.float32, np.float64) else np.float64
+        Ns, Nt, Xt, Xs, Xn, _ = self._arrays(Xt, Xs, Xn, None, dtype, need_v=False)
+        rows, cols = Ns * self._k0, Nt * self._k1
+        if M is None or M.shape != (rows, cols) or M.dtype != dtype or not M.flags.c_contiguous:
+            M = np.zeros((rows, cols), dtype=dtype)  # ReInit + SetZero (:220-223)
+        _check(load_library().sctl_cuda_kernel_matrix(self.kernel_id, M.itemsize, int(digits), Ns, Nt, _np_ptr(Xs), _np_ptr(Xn), _np_ptr(Xt), _np_ptr(M), cols))
+        return M
+
+
+Laplace3D_FxU = GenericKernel("Laplace3D_FxU")
+Laplace3D_DxU = GenericKernel("Laplace3D_DxU")
+Laplace3D_FxdU = GenericKernel("Laplace3D_FxdU")
+Stokes3D_FxU = GenericKernel("Stokes3D_FxU")
+Stokes3D_DxU = GenericKernel("Stokes3D_DxU")
+KERNELS = {"Laplace3D_FxU": Laplace3D_FxU, "Laplace3D_DxU": Laplace3D_DxU, "Laplace3D_FxdU": Laplace3D_FxdU, "Stokes3D_FxU": Stokes3D_FxU,
+           "Stokes3D_DxU": Stokes3D_DxU}

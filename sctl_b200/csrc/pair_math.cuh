@@ -1,0 +1,214 @@
+// Device twins of the reference micro-kernels and of approx_rsqrt<digits>.
+//
+// Reference semantics (paths relative to /root/reference/include/sctl/):
+//   kernel_impl::Laplace3D_FxU/DxU/FxdU, Stokes3D_FxU/DxU      kernel_functions.hpp:32-218
+//   approx_rsqrt<digits>(r2, r2 > 0): seed + Newton, 0 on masked lanes   vec.txx:375-382, intrin-wrapper.hpp:540-559
+//   pair update dX = xt - xs; fused uKerApply or uKerMatrix + FMA          generic-kernel.txx:107-121
+//
+// This is not a translation of those bodies: the arithmetic is re-associated for the B200 FP64 pipe
+// (fewest DADD/DMUL/DFMA per pair; everything that is not FP64 goes to the ALU/XU pipes that issue in the
+// FP64 pipe's shadow), and sources arrive as packed records (see source_pack.cuh) instead of three AoS arrays.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sctl_cuda {
+
+enum : int { LAPLACE3D_FXU = 0, LAPLACE3D_DXU = 1, LAPLACE3D_FXDU = 2, STOKES3D_FXU = 3, STOKES3D_DXU = 4, NUM_KERNELS = 5 };
+
+// How far the seed is refined; chosen on the host from `digits` (see rsq_mode_for_digits()).
+enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// Masked reciprocal square root:  r2 > 0 ? r2^(-1/2) : 0     (approx_rsqrt<digits>(r2, r2 > 0))
+// ------------------------------------------------------------------------------------------------
+
+// FP64.  Seed = MUFU.RSQ64H on the high word (one XU-pipe instruction, valid over the whole normal
+// double range, ~2^-20 relative error because the low mantissa word is ignored).  Refinement runs on
+// the FP64 pipe with the residual e = 1 - x*y0^2:
+//   RSQ_NEWTON: y = y0 + (y0*e)*(1/2)                 4 FP64 instr, error ~ 3/8 e^2  (~1e-12)
+//   RSQ_CUBIC : y = y0 + (y0*e)*(1/2 + 3/8 e)         5 FP64 instr, error ~ 5/16 e^3 (< 1 ulp)
+// SCTL's AVX-512 recipe (14-bit seed, 2 Newton steps, deferred scaling) costs 7.
+// Mask: like _mm512_maskz_rsqrt14_pd in the reference (intrin-wrapper.hpp:3403) the SEED is zeroed and the
+// refinement then keeps it zero (e = 1, y0*e = 0).  The test is one integer range check on the high word
+// (ALU pipe, no branch): zero, NaN, Inf and subnormal r2 are masked.  Subnormal r2 (|dx| < 1.5e-154) is
+// treated as coincident; the reference overflows to Inf/NaN there for every kernel but Laplace FxU.
+template <int MODE> __device__ __forceinline__ double rsqrt_masked(double x) {
+  const int hi = __double2hiint(x);
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+  const bool ok = (unsigned)(hi - 0x00100000) < 0x7fe00000u;  // positive, normal, finite
+  y0 = __hiloint2double(ok ? __double2hiint(y0) : 0, 0);
+  if (MODE == RSQ_SEED) return y0;
+  const double e = fma(-x, y0 * y0, 1.0);
+  const double ye = y0 * e;
+  if (MODE == RSQ_NEWTON) return fma(ye, 0.5, y0);
+  return fma(fma(e, 0.375, 0.5), ye, y0);
+}
+
+// FP32.  Seed = MUFU.RSQ (2^-22 relative error): that already meets approx_rsqrt<digits<=6>, which is what the
+// reference computes for float by default (digits = (int)(23*0.30103) = 6, vec.txx:376).  digits >= 7 adds one
+// Newton step on the FP32 pipe.  Same masking rule as FP64 (subnormal r2 means |dx| < 1.1e-19).
+template <int MODE> __device__ __forceinline__ float rsqrt_masked(float x) {
+  float y0;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
+  const bool ok = __float_as_uint(x) - 0x00800000u < 0x7f000000u;  // positive, normal, finite
+  y0 = ok ? y0 : 0.0f;
+  if (MODE == RSQ_SEED) return y0;
+  const float e = fmaf(-x, y0 * y0, 1.0f);
+  return fmaf(y0 * e, 0.5f, y0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel traits
+// ------------------------------------------------------------------------------------------------
+// K0/K1/ND: GenericKernel's KDIM0/KDIM1/N_DIM (generic-kernel.hpp:22-41).  FLOPS: uKernel::FLOPS().
+// PACK: reals per packed source record before padding (source_pack.cuh).  F_ALG: SURVEY.md section 8(d).
+template <int KID> struct KerTraits;
+template <> struct KerTraits<LAPLACE3D_FXU>  { static constexpr int K0 = 1, K1 = 1, ND = 0, PACK = 4, FLOPS = 6,  F_ALG = 11; };
+template <> struct KerTraits<LAPLACE3D_DXU>  { static constexpr int K0 = 1, K1 = 1, ND = 3, PACK = 6, FLOPS = 14, F_ALG = 19; };
+template <> struct KerTraits<LAPLACE3D_FXDU> { static constexpr int K0 = 1, K1 = 3, ND = 0, PACK = 4, FLOPS = 11, F_ALG = 18; };
+template <> struct KerTraits<STOKES3D_FXU>   { static constexpr int K0 = 3, K1 = 3, ND = 0, PACK = 6, FLOPS = 23, F_ALG = 29; };
+template <> struct KerTraits<STOKES3D_DXU>   { static constexpr int K0 = 3, K1 = 3, ND = 3, PACK = 9, FLOPS = 26, F_ALG = 30; };
+
+// Reals per record, padded so that every record is a whole number of 16-byte words (LDS.128 / bulk-copy unit).
+template <class Real, int KID> struct RecTraits {
+  static constexpr int W = 16 / (int)sizeof(Real);
+  static constexpr int REC = (KerTraits<KID>::PACK + W - 1) / W * W;
+};
+
+struct KernelInfo { int k0, k1, nd, flops, f_alg; const char* name; };
+__host__ inline KernelInfo kernel_info(int kid) {
+  switch (kid) {
+    case LAPLACE3D_FXU:  return {1, 1, 0, 6, 11, "Laplace3D-FxU"};
+    case LAPLACE3D_DXU:  return {1, 1, 3, 14, 19, "Laplace3D-DxU"};
+    case LAPLACE3D_FXDU: return {1, 3, 0, 11, 18, "Laplace3D-FxdU"};
+    case STOKES3D_FXU:   return {3, 3, 0, 23, 29, "Stokes3D-FxU"};
+    case STOKES3D_DXU:   return {3, 3, 3, 26, 30, "Stokes3D-DxU"};
+    default:             return {0, 0, 0, 0, 0, nullptr};
+  }
+}
+
+// uKerScaleFactor<Real>() (kernel_functions.hpp:40-42, 69-71, 89-91, 133-135, 188-190), evaluated in Real.
+template <class Real> __host__ __device__ inline Real scale_factor(int kid) {
+  const Real pi = (Real)3.14159265358979323846264338327950288L;
+  switch (kid) {
+    case LAPLACE3D_FXU: case LAPLACE3D_DXU: return 1 / (4 * pi);
+    case LAPLACE3D_FXDU: return -1 / (4 * pi);
+    case STOKES3D_FXU: return 1 / (8 * pi);
+    default: return 3 / (4 * pi);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused pair update:  acc[K1] += K(dx; n) f   (unscaled), given dx = xt - xs and rinv.
+// `s` points at the packed source record held in registers: s[0..2] = xs, s[3..] = payload.
+// FP64-pipe instruction counts per pair (after the 6-instruction prefix dx, r2 and the rsqrt):
+//   Laplace FxU 1 | Laplace DxU 6 | Laplace FxdU 6 | Stokes FxU 11 | Stokes DxU 14
+// ------------------------------------------------------------------------------------------------
+template <int KID, class Real> struct PairApply;
+
+// u = rinv                                   (kernel_functions.hpp:43-47)
+template <class Real> struct PairApply<LAPLACE3D_FXU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[1], const Real (&dx)[3], Real rinv, const Real* s) {
+    acc[0] = fma(rinv, s[3], acc[0]);
+  }
+};
+// u = (r.n) rinv^3; the record carries g = f*n so the pair costs one dot product      (:72-78)
+template <class Real> struct PairApply<LAPLACE3D_DXU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[1], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv3 = rinv * rinv * rinv;
+    const Real d = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3]));
+    acc[0] = fma(d, rinv3, acc[0]);
+  }
+};
+// v_i += r_i (f rinv^3)                      (fused apply, :102-110)
+template <class Real> struct PairApply<LAPLACE3D_FXDU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real t = (rinv * rinv) * (rinv * s[3]);
+    acc[0] = fma(dx[0], t, acc[0]);
+    acc[1] = fma(dx[1], t, acc[1]);
+    acc[2] = fma(dx[2], t, acc[2]);
+  }
+};
+// v_i += f_i rinv + r_i (f.r) rinv^3  =  rinv (f_i + r_i (f.r) rinv^2)      (fused apply, :166-176)
+template <class Real> struct PairApply<STOKES3D_FXU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    const Real d = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3]));
+    const Real c = d * rinv2;
+    acc[0] = fma(rinv, fma(dx[0], c, s[3]), acc[0]);
+    acc[1] = fma(rinv, fma(dx[1], c, s[4]), acc[1]);
+    acc[2] = fma(rinv, fma(dx[2], c, s[5]), acc[2]);
+  }
+};
+// v_i += r_i (f.r)(r.n) rinv^5              (fused apply, :205-217)
+template <class Real> struct PairApply<STOKES3D_DXU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv5 = (rinv2 * rinv2) * rinv;
+    const Real df = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3]));
+    const Real dn = fma(dx[2], s[8], fma(dx[1], s[7], dx[0] * s[6]));
+    const Real t = (df * dn) * rinv5;
+    acc[0] = fma(dx[0], t, acc[0]);
+    acc[1] = fma(dx[1], t, acc[1]);
+    acc[2] = fma(dx[2], t, acc[2]);
+  }
+};
+
+// One source-target pair, starting from coordinates.
+template <int KID, int RSQ, class Real>
+__device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], const Real (&xt)[3], const Real* s) {
+  Real dx[3];
+  dx[0] = xt[0] - s[0];
+  dx[1] = xt[1] - s[1];
+  dx[2] = xt[2] - s[2];
+  const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
+  const Real rinv = rsqrt_masked<RSQ>(r2);
+  PairApply<KID, Real>::run(acc, dx, rinv, s);
+}
+
+// uKerMatrix twin: u[K0][K1] (unscaled) for one displacement, with the raw normal (KernelMatrix path,
+// generic-kernel.txx:213-329, never uses the fused apply).
+template <int KID, class Real> struct PairMatrix;
+template <class Real> struct PairMatrix<LAPLACE3D_FXU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) { u[0] = rinv; }
+};
+template <class Real> struct PairMatrix<LAPLACE3D_DXU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rdotn = fma(dx[2], n[2], fma(dx[1], n[1], dx[0] * n[0]));
+    u[0] = rdotn * (rinv * rinv * rinv);
+  }
+};
+template <class Real> struct PairMatrix<LAPLACE3D_FXDU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv3 = rinv * rinv * rinv;
+    u[0] = dx[0] * rinv3; u[1] = dx[1] * rinv3; u[2] = dx[2] * rinv3;
+  }
+};
+template <class Real> struct PairMatrix<STOKES3D_FXU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv3 = rinv * rinv * rinv;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const Real a = dx[i] * rinv3;
+#pragma unroll
+      for (int j = 0; j < 3; j++) u[i * 3 + j] = (i == j) ? fma(a, dx[j], rinv) : a * dx[j];
+    }
+  }
+};
+template <class Real> struct PairMatrix<STOKES3D_DXU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv5 = (rinv2 * rinv2) * rinv;
+    const Real c = fma(dx[2], n[2], fma(dx[1], n[1], dx[0] * n[0])) * rinv5;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const Real a = dx[i] * c;
+#pragma unroll
+      for (int j = 0; j < 3; j++) u[i * 3 + j] = a * dx[j];
+    }
+  }
+};
+
+}  // namespace sctl_cuda

@@ -1,0 +1,739 @@
+// libsctl_cuda.so -- C ABI (include/sctl_cuda.h) over the sm_100a kernels in eval_kernel.cuh / kmat_kernel.cuh.
+// Host side of the drop-in for GenericKernel<uKernel>::Eval / KernelMatrix
+// (reference: include/sctl/generic-kernel.txx:102-329).  No CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen'ed in sctl_cuda_init(n > 1)
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/sctl_cuda.h"
+#include "eval_kernel.cuh"
+#include "kmat_kernel.cuh"
+
+using namespace sctl_cuda;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+thread_local std::string tl_err;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  tl_err = buf;
+  return 1;
+}
+
+#define CU_TRY(expr)                                                                          \
+  do {                                                                                        \
+    cudaError_t e_ = (expr);                                                                  \
+    if (e_ != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// per-thread state
+// ---------------------------------------------------------------------------------------------
+constexpr int MAX_DEV = 16;
+
+struct ThreadState {
+  cudaStream_t stream[MAX_DEV] = {};
+  cudaEvent_t ev[MAX_DEV][4] = {};
+  double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
+  int grid_x = 0, grid_y = 0, threads = 0, smem = 0, ctas_per_sm = 0, n_launches = 0;
+  double wave_eff = 0;
+  ~ThreadState() {
+    // streams/events are left to the driver at process exit (destroying them after the primary
+    // context is gone is an error); threads that end early leak a few handles at most.
+  }
+};
+thread_local ThreadState tl;
+
+struct DeviceInfo {
+  int sms = 0;
+  bool pool_configured = false;
+};
+
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+struct Global {
+  std::mutex mu;
+  int n_gpus = 0;  // 0 = not initialised
+  DeviceInfo dev[MAX_DEV];
+  NcclApi nccl;
+  ncclComm_t comms[MAX_DEV] = {};
+  bool have_comms = false;
+  // sharded (multi-GPU) host calls run one at a time on persistent per-device streams
+  std::mutex multi_mu;
+  cudaStream_t mstream[MAX_DEV] = {};
+  cudaEvent_t mev[MAX_DEV][4] = {};
+};
+Global g;
+
+int ensure_device_info(int dev) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  {
+    if (!g.dev[dev].pool_configured) {
+      cudaDeviceProp prop;
+      CU_TRY(cudaGetDeviceProperties(&prop, dev));
+      if (prop.major < 10) return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+      g.dev[dev].sms = prop.multiProcessorCount;
+      cudaMemPool_t pool;
+      CU_TRY(cudaDeviceGetDefaultMemPool(&pool, dev));
+      uint64_t thresh = UINT64_MAX;  // keep scratch cached between calls
+      CU_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+      g.dev[dev].pool_configured = true;
+    }
+  }
+  return 0;
+}
+
+int ensure_device(int dev) {
+  if (ensure_device_info(dev)) return 1;
+  if (!tl.stream[dev]) {
+    int cur;
+    CU_TRY(cudaGetDevice(&cur));
+    CU_TRY(cudaSetDevice(dev));
+    CU_TRY(cudaStreamCreateWithFlags(&tl.stream[dev], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) CU_TRY(cudaEventCreate(&tl.ev[dev][i]));
+    CU_TRY(cudaSetDevice(cur));
+  }
+  return 0;
+}
+
+int visible_devices() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// digits -> refinement of the reciprocal-square-root seed  (approx_rsqrt<digits>, vec.txx:375-382)
+// ---------------------------------------------------------------------------------------------
+// FP64: seed (MUFU.RSQ64H) is good to ~2^-20 -> 5 digits; one Newton step ~1.4e-12 -> 11 digits; the cubic
+// step is correct to < 1 ulp.  FP32: MUFU.RSQ is good to 2^-22 -> 6 digits; one Newton step -> 7.
+template <class Real> int rsq_mode_for_digits(int digits) {
+  if (sizeof(Real) == 8) {
+    if (digits < 0 || digits >= 16) digits = 15;  // (Integer)(52*0.30103)
+    return digits <= 5 ? RSQ_SEED : digits <= 11 ? RSQ_NEWTON : RSQ_CUBIC;
+  } else {
+    if (digits < 0 || digits >= 16) digits = 6;  // (Integer)(23*0.30103)
+    return digits <= 6 ? RSQ_SEED : RSQ_NEWTON;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch configurations
+// ---------------------------------------------------------------------------------------------
+// MAIN: many targets.  FEW: few targets -- all warps of a CTA share 32*T targets and split the sources.
+template <class Real> struct Tune;
+template <> struct Tune<double> {
+  static constexpr int T = 2, NW = 8, TILE = 256, STAGES = 3, MINB = 2;
+  static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 256, FEW_STAGES = 3, FEW_MINB = 2;
+};
+template <> struct Tune<float> {
+  static constexpr int T = 4, NW = 8, TILE = 512, STAGES = 3, MINB = 2;
+  static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 512, FEW_STAGES = 3, FEW_MINB = 2;
+};
+
+struct OccCache {
+  std::mutex mu;
+  int ctas[MAX_DEV] = {};
+};
+
+template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES, int MINB>
+int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, cudaStream_t stream, int min_chunk, int max_split) {
+  using Cfg = EvalConfig<Real, KID, T, NW, R, RSQ, TILE, STAGES>;
+  auto kern = eval_pairs_kernel<Real, KID, T, NW, R, RSQ, TILE, STAGES, MINB>;
+  static OccCache occ;
+  int ctas_per_sm;
+  {
+    std::lock_guard<std::mutex> lk(occ.mu);
+    if (!occ.ctas[dev]) {
+      CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+      int nb = 0;
+      CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, Cfg::THREADS, Cfg::SMEM_BYTES));
+      if (nb < 1) return fail("eval kernel does not fit on an SM (threads %d, smem %zu)", Cfg::THREADS, Cfg::SMEM_BYTES);
+      occ.ctas[dev] = nb;
+    }
+    ctas_per_sm = occ.ctas[dev];
+  }
+  const int slots = g.dev[dev].sms * ctas_per_sm;
+  EvalPlan plan = plan_eval(Ns, Nt, Cfg::TPB, slots, min_chunk, max_split);
+  if (plan.n_tblocks > 2147483647LL) return fail("too many target blocks");
+
+  EvalArgs<Real> a;
+  a.pack = pack;
+  a.r_trg = r_trg;
+  a.v_trg = v_trg;
+  a.partial = nullptr;
+  a.Ns = Ns;
+  a.Nt = Nt;
+  a.chunk = plan.chunk;
+  a.n_split = plan.n_split;
+  a.scale = scale_factor<Real>(KID);
+  constexpr int K1 = KerTraits<KID>::K1;
+  int n_launches = 1;
+  if (plan.n_split > 1) CU_TRY(cudaMallocAsync((void**)&a.partial, sizeof(Real) * (size_t)plan.n_split * Nt * K1, stream));
+  dim3 grid((unsigned)plan.n_tblocks, (unsigned)plan.n_split);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
+  CU_TRY(cudaGetLastError());
+  if (plan.n_split > 1) {
+    const int64_t n = Nt * K1;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
+    reduce_partials_kernel<Real><<<blocks, 256, 0, stream>>>(n, plan.n_split, a.partial, a.scale, v_trg);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaFreeAsync(a.partial, stream));
+    n_launches = 2;
+  }
+  tl.grid_x = (int)grid.x;
+  tl.grid_y = (int)grid.y;
+  tl.threads = Cfg::THREADS;
+  tl.smem = (int)Cfg::SMEM_BYTES;
+  tl.ctas_per_sm = ctas_per_sm;
+  tl.n_launches = n_launches;
+  tl.wave_eff = plan.wave_eff;
+  return 0;
+}
+
+// few-target threshold: below this many targets the MAIN grid cannot fill the GPU even with source splitting
+constexpr int64_t FEW_TARGETS = 2048;
+
+template <class Real, int KID, int RSQ>
+int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
+  using Tn = Tune<Real>;
+  constexpr int REC = RecTraits<Real, KID>::REC;
+  Real* pack = nullptr;
+  CU_TRY(cudaMallocAsync((void**)&pack, sizeof(Real) * (size_t)Ns * REC, stream));
+  {
+    const int blocks = (int)std::min<int64_t>((Ns + 255) / 256, 8192);
+    pack_sources_kernel<Real, KID><<<blocks, 256, 0, stream>>>(Ns, r_src, n_src, v_src, pack);
+    CU_TRY(cudaGetLastError());
+  }
+  int rc;
+  if (Nt <= FEW_TARGETS)
+    rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, Tn::FEW_TILE, 1024);
+  else
+    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, 8 * Tn::TILE, 64);
+  if (rc) {
+    cudaFreeAsync(pack, stream);
+    return rc;
+  }
+  tl.n_launches += 1;  // the pack kernel
+  CU_TRY(cudaFreeAsync(pack, stream));
+  return 0;
+}
+
+template <class Real, int KID>
+int eval_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
+  switch (rsq_mode_for_digits<Real>(digits)) {
+    case RSQ_SEED: return eval_device_t<Real, KID, RSQ_SEED>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+    case RSQ_NEWTON: return eval_device_t<Real, KID, RSQ_NEWTON>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+    default:
+      if (sizeof(Real) == 4) return eval_device_t<Real, KID, RSQ_NEWTON>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+      return eval_device_t<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON)>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+  }
+}
+
+template <class Real>
+int eval_device_r(int dev, int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, cudaStream_t stream) {
+#define SCTL_CUDA_CASE(K) \
+  case K: return eval_device_k<Real, K>(dev, digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)v_src, (const Real*)r_trg, (Real*)v_trg, stream);
+  switch (kid) {
+    SCTL_CUDA_CASE(LAPLACE3D_FXU)
+    SCTL_CUDA_CASE(LAPLACE3D_DXU)
+    SCTL_CUDA_CASE(LAPLACE3D_FXDU)
+    SCTL_CUDA_CASE(STOKES3D_FXU)
+    SCTL_CUDA_CASE(STOKES3D_DXU)
+    default: return fail("unknown kernel id %d", kid);
+  }
+#undef SCTL_CUDA_CASE
+}
+
+int check_common(int kid, int real_bytes, int64_t Ns, int64_t Nt) {
+  if (kid < 0 || kid >= NUM_KERNELS) return fail("unknown kernel id %d", kid);
+  if (real_bytes != 8 && real_bytes != 4) return fail("real_bytes must be 8 (double) or 4 (float), got %d", real_bytes);
+  if (Ns < 0 || Nt < 0) return fail("negative size (Ns=%lld, Nt=%lld)", (long long)Ns, (long long)Nt);
+  return 0;
+}
+
+int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, cudaStream_t stream) {
+  const KernelInfo ki = kernel_info(kid);
+  tl.n_launches = 0;
+  if (Ns == 0 || Nt == 0) return 0;  // nothing to add
+  if (!r_src || !v_src || !r_trg || !v_trg) return fail("null array pointer");
+  if (ki.nd && !n_src) return fail("kernel %s needs source normals (n_src is NULL)", ki.name);
+  if (real_bytes == 8) return eval_device_r<double>(dev, kid, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+  return eval_device_r<float>(dev, kid, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// KernelMatrix
+// ---------------------------------------------------------------------------------------------
+template <class Real, int KID>
+int kmat_device_k(int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, cudaStream_t stream) {
+  constexpr int BT = 128;
+  dim3 grid((unsigned)((Nt + BT - 1) / BT), (unsigned)std::min<int64_t>(Ns, 32768));
+  const Real scale = scale_factor<Real>(KID);
+  switch (rsq_mode_for_digits<Real>(digits)) {
+    case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale); break;
+    case RSQ_NEWTON: kernel_matrix_kernel<Real, KID, RSQ_NEWTON, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale); break;
+    default: kernel_matrix_kernel<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON), BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale); break;
+  }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <class Real>
+int kmat_device_r(int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, cudaStream_t stream) {
+#define SCTL_CUDA_CASE(K) \
+  case K: return kmat_device_k<Real, K>(digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)r_trg, (Real*)M, ldM, stream);
+  switch (kid) {
+    SCTL_CUDA_CASE(LAPLACE3D_FXU)
+    SCTL_CUDA_CASE(LAPLACE3D_DXU)
+    SCTL_CUDA_CASE(LAPLACE3D_FXDU)
+    SCTL_CUDA_CASE(STOKES3D_FXU)
+    SCTL_CUDA_CASE(STOKES3D_DXU)
+    default: return fail("unknown kernel id %d", kid);
+  }
+#undef SCTL_CUDA_CASE
+}
+
+int kmat_device_any(int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, cudaStream_t stream) {
+  const KernelInfo ki = kernel_info(kid);
+  if (Ns == 0 || Nt == 0) return 0;
+  if (!r_src || !r_trg || !M) return fail("null array pointer");
+  if (ki.nd && !n_src) return fail("kernel %s needs source normals (n_src is NULL)", ki.name);
+  if (ldM < Nt * ki.k1) return fail("ldM (%lld) smaller than Nt*K1 (%lld)", (long long)ldM, (long long)(Nt * ki.k1));
+  if (real_bytes == 8) return kmat_device_r<double>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, stream);
+  return kmat_device_r<float>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// small device utilities
+// ---------------------------------------------------------------------------------------------
+template <class Real, int MODE> __global__ void rsqrt_test_kernel(int64_t n, const Real* x, Real* y) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] = rsqrt_masked<MODE>(x[i]);
+}
+
+template <class Real> __global__ void __launch_bounds__(256) fma_peak_kernel(int iters, Real* out, Real seed) {
+  Real a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const Real m = (Real)0.999999, c = (Real)1e-6;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+      a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+  }
+  const Real s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == (Real)-1) out[0] = s;  // never true; keeps the chains alive
+}
+
+template <class Real> int fma_peak_t(double ms, double* tflops) {
+  int dev;
+  CU_TRY(cudaGetDevice(&dev));
+  if (ensure_device(dev)) return 1;
+  cudaStream_t st = tl.stream[dev];
+  Real* out;
+  CU_TRY(cudaMallocAsync((void**)&out, sizeof(Real), st));
+  const int blocks = g.dev[dev].sms * 8, threads = 256;
+  int iters = 2000;
+  float t = 0;
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++) {
+    CU_TRY(cudaEventRecord(tl.ev[dev][0], st));
+    fma_peak_kernel<Real><<<blocks, threads, 0, st>>>(iters, out, (Real)0.5);
+    CU_TRY(cudaEventRecord(tl.ev[dev][1], st));
+    CU_TRY(cudaEventSynchronize(tl.ev[dev][1]));
+    CU_TRY(cudaEventElapsedTime(&t, tl.ev[dev][0], tl.ev[dev][1]));
+    const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;
+    if (rep > 0) best = std::max(best, flop / (t * 1e-3) * 1e-12);
+    if (t < ms && rep < 4) iters = (int)std::min<double>(2.0e6, iters * std::max(1.5, ms / std::max(t, 0.01f)));
+  }
+  CU_TRY(cudaFreeAsync(out, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  *tflops = best;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-pointer paths
+// ---------------------------------------------------------------------------------------------
+int current_device_ready(int* dev) {
+  if (visible_devices() < 1) return fail("no CUDA device available (libsctl_cuda has no CPU fallback)");
+  CU_TRY(cudaGetDevice(dev));
+  if (*dev >= MAX_DEV) return fail("device index %d too large", *dev);
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.n_gpus == 0) g.n_gpus = 1;
+  }
+  return ensure_device(*dev);
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  int alloc(size_t bytes, cudaStream_t s) {
+    st = s;
+    if (bytes == 0) return 0;
+    CU_TRY(cudaMallocAsync(&p, bytes, s));
+    return 0;
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+
+// One GPU: upload everything, run, download the target range [t0, t1).
+int eval_host_one(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t t0, int64_t t1, const char* r_src, const char* n_src, const char* v_src,
+                  const char* r_trg, char* v_trg, bool timing) {
+  const KernelInfo ki = kernel_info(kid);
+  const size_t rb = (size_t)real_bytes;
+  const int64_t nt = t1 - t0;
+  CU_TRY(cudaSetDevice(dev));
+  if (ensure_device(dev)) return 1;
+  cudaStream_t st = tl.stream[dev];
+  DevBuf d_rs, d_ns, d_vs, d_rt, d_vt;
+  if (d_rs.alloc(rb * Ns * 3, st) || d_vs.alloc(rb * Ns * ki.k0, st) || d_rt.alloc(rb * nt * 3, st) || d_vt.alloc(rb * nt * ki.k1, st)) return 1;
+  if (ki.nd && d_ns.alloc(rb * Ns * ki.nd, st)) return 1;
+  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][0], st));
+  CU_TRY(cudaMemcpyAsync(d_rs.p, r_src, rb * Ns * 3, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(d_vs.p, v_src, rb * Ns * ki.k0, cudaMemcpyHostToDevice, st));
+  if (ki.nd) CU_TRY(cudaMemcpyAsync(d_ns.p, n_src, rb * Ns * ki.nd, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg + rb * t0 * 3, rb * nt * 3, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(d_vt.p, v_trg + rb * t0 * ki.k1, rb * nt * ki.k1, cudaMemcpyHostToDevice, st));
+  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][1], st));
+  if (eval_device_any(dev, kid, real_bytes, digits, Ns, nt, d_rs.p, d_ns.p, d_vs.p, d_rt.p, d_vt.p, st)) return 1;
+  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][2], st));
+  CU_TRY(cudaMemcpyAsync(v_trg + rb * t0 * ki.k1, d_vt.p, rb * nt * ki.k1, cudaMemcpyDeviceToHost, st));
+  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][3], st));
+  CU_TRY(cudaStreamSynchronize(st));
+  if (timing) {
+    float a = 0, b = 0, c = 0;
+    CU_TRY(cudaEventElapsedTime(&a, tl.ev[dev][0], tl.ev[dev][1]));
+    CU_TRY(cudaEventElapsedTime(&b, tl.ev[dev][1], tl.ev[dev][2]));
+    CU_TRY(cudaEventElapsedTime(&c, tl.ev[dev][2], tl.ev[dev][3]));
+    tl.h2d_ms = a;
+    tl.kernel_ms = b;
+    tl.d2h_ms = c;
+  }
+  return 0;
+}
+
+// P GPUs of this process: GPU p uploads source slice p and target shard p; slices are replicated with one
+// grouped set of ncclBroadcast (an all-gather with ragged counts) over NVLink; each GPU evaluates its shard
+// against all sources and downloads its slice of v_trg.  No reduction, so per-target summation order is the
+// single-GPU order.  (Reference analogue: ParticleFMM::EvalDirect's np-step ring, fmm-wrapper.txx:551-623.)
+struct ShardResult {
+  int rc = 0;
+  std::string err;
+  double h2d = 0, ker = 0, d2h = 0;
+};
+
+void eval_host_shard(int p, int P, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const char* r_src, const char* n_src, const char* v_src,
+                     const char* r_trg, char* v_trg, ShardResult* res) {
+  auto body = [&]() -> int {
+    const KernelInfo ki = kernel_info(kid);
+    const size_t rb = (size_t)real_bytes;
+    const int64_t t0 = Nt * p / P, t1 = Nt * (p + 1) / P, nt = t1 - t0;
+    CU_TRY(cudaSetDevice(p));
+    cudaStream_t st = g.mstream[p];
+    cudaEvent_t* ev = g.mev[p];
+    DevBuf d_rs, d_ns, d_vs, d_rt, d_vt;
+    if (d_rs.alloc(rb * Ns * 3, st) || d_vs.alloc(rb * Ns * ki.k0, st) || d_rt.alloc(rb * std::max<int64_t>(nt, 1) * 3, st) ||
+        d_vt.alloc(rb * std::max<int64_t>(nt, 1) * ki.k1, st))
+      return 1;
+    if (ki.nd && d_ns.alloc(rb * Ns * ki.nd, st)) return 1;
+    CU_TRY(cudaEventRecord(ev[0], st));
+    const int64_t s0 = Ns * p / P, s1 = Ns * (p + 1) / P;
+    CU_TRY(cudaMemcpyAsync((char*)d_rs.p + rb * s0 * 3, r_src + rb * s0 * 3, rb * (s1 - s0) * 3, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync((char*)d_vs.p + rb * s0 * ki.k0, v_src + rb * s0 * ki.k0, rb * (s1 - s0) * ki.k0, cudaMemcpyHostToDevice, st));
+    if (ki.nd) CU_TRY(cudaMemcpyAsync((char*)d_ns.p + rb * s0 * ki.nd, n_src + rb * s0 * ki.nd, rb * (s1 - s0) * ki.nd, cudaMemcpyHostToDevice, st));
+    if (nt) {
+      CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg + rb * t0 * 3, rb * nt * 3, cudaMemcpyHostToDevice, st));
+      CU_TRY(cudaMemcpyAsync(d_vt.p, v_trg + rb * t0 * ki.k1, rb * nt * ki.k1, cudaMemcpyHostToDevice, st));
+    }
+    // replicate the source slices: root q broadcasts its slice into the same offsets on every GPU
+    const ncclDataType_t dt = real_bytes == 8 ? ncclFloat64 : ncclFloat32;
+    ncclResult_t nr = g.nccl.GroupStart();
+    for (int q = 0; q < P && nr == ncclSuccess; q++) {
+      const int64_t q0 = Ns * q / P, q1 = Ns * (q + 1) / P;
+      if (q1 == q0) continue;
+      char* a = (char*)d_rs.p + rb * q0 * 3;
+      nr = g.nccl.Broadcast(a, a, (size_t)(q1 - q0) * 3, dt, q, g.comms[p], st);
+      if (nr != ncclSuccess) break;
+      char* b = (char*)d_vs.p + rb * q0 * ki.k0;
+      nr = g.nccl.Broadcast(b, b, (size_t)(q1 - q0) * ki.k0, dt, q, g.comms[p], st);
+      if (nr != ncclSuccess) break;
+      if (ki.nd) {
+        char* c = (char*)d_ns.p + rb * q0 * ki.nd;
+        nr = g.nccl.Broadcast(c, c, (size_t)(q1 - q0) * ki.nd, dt, q, g.comms[p], st);
+      }
+    }
+    ncclResult_t ne = g.nccl.GroupEnd();
+    if (nr != ncclSuccess || ne != ncclSuccess) return fail("NCCL broadcast failed: %s", g.nccl.GetErrorString(nr != ncclSuccess ? nr : ne));
+    CU_TRY(cudaEventRecord(ev[1], st));
+    if (nt && eval_device_any(p, kid, real_bytes, digits, Ns, nt, d_rs.p, d_ns.p, d_vs.p, d_rt.p, d_vt.p, st)) return 1;
+    CU_TRY(cudaEventRecord(ev[2], st));
+    if (nt) CU_TRY(cudaMemcpyAsync(v_trg + rb * t0 * ki.k1, d_vt.p, rb * nt * ki.k1, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaEventRecord(ev[3], st));
+    CU_TRY(cudaStreamSynchronize(st));
+    float a = 0, b = 0, c = 0;
+    CU_TRY(cudaEventElapsedTime(&a, ev[0], ev[1]));
+    CU_TRY(cudaEventElapsedTime(&b, ev[1], ev[2]));
+    CU_TRY(cudaEventElapsedTime(&c, ev[2], ev[3]));
+    res->h2d = a;
+    res->ker = b;
+    res->d2h = c;
+    return 0;
+  };
+  res->rc = body();
+  if (res->rc) res->err = tl_err;
+}
+
+// below this many pairs one GPU finishes before the extra launches and the broadcast pay off
+constexpr double MULTI_GPU_MIN_PAIRS = 1.0e9;
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int sctl_cuda_device_count(void) { return visible_devices(); }
+
+const char* sctl_cuda_last_error(void) { return tl_err.c_str(); }
+
+int sctl_cuda_num_gpus(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  return g.n_gpus;
+}
+
+int sctl_cuda_init(int n_gpus) {
+  const int vis = visible_devices();
+  if (vis < 1) return fail("no CUDA device available (libsctl_cuda has no CPU fallback)");
+  if (n_gpus < 0 || n_gpus > vis) return fail("requested %d GPUs, %d visible", n_gpus, vis);
+  if (n_gpus == 0) n_gpus = vis;
+  if (n_gpus > MAX_DEV) n_gpus = MAX_DEV;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.have_comms && g.n_gpus == n_gpus) return 0;
+  }
+  if (sctl_cuda_finalize()) return 1;
+  if (n_gpus > 1) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.nccl.handle) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+      if (!h) return fail("cannot load NCCL: %s", dlerror());
+      g.nccl.handle = h;
+      g.nccl.CommInitAll = (decltype(g.nccl.CommInitAll))dlsym(h, "ncclCommInitAll");
+      g.nccl.CommDestroy = (decltype(g.nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+      g.nccl.Broadcast = (decltype(g.nccl.Broadcast))dlsym(h, "ncclBroadcast");
+      g.nccl.GroupStart = (decltype(g.nccl.GroupStart))dlsym(h, "ncclGroupStart");
+      g.nccl.GroupEnd = (decltype(g.nccl.GroupEnd))dlsym(h, "ncclGroupEnd");
+      g.nccl.GetErrorString = (decltype(g.nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+      if (!g.nccl.CommInitAll || !g.nccl.CommDestroy || !g.nccl.Broadcast || !g.nccl.GroupStart || !g.nccl.GroupEnd || !g.nccl.GetErrorString)
+        return fail("NCCL library lacks a required symbol");
+    }
+    int devs[MAX_DEV];
+    for (int i = 0; i < n_gpus; i++) devs[i] = i;
+    ncclResult_t r = g.nccl.CommInitAll(g.comms, n_gpus, devs);
+    if (r != ncclSuccess) return fail("ncclCommInitAll(%d) failed: %s", n_gpus, g.nccl.GetErrorString(r));
+    g.have_comms = true;
+  }
+  int cur = 0;
+  CU_TRY(cudaGetDevice(&cur));
+  for (int i = 0; i < n_gpus; i++) {
+    if (ensure_device_info(i)) return 1;
+    if (n_gpus > 1 && !g.mstream[i]) {
+      CU_TRY(cudaSetDevice(i));
+      CU_TRY(cudaStreamCreateWithFlags(&g.mstream[i], cudaStreamNonBlocking));
+      for (int k = 0; k < 4; k++) CU_TRY(cudaEventCreate(&g.mev[i][k]));
+    }
+  }
+  CU_TRY(cudaSetDevice(cur));
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.n_gpus = n_gpus;
+  return 0;
+}
+
+int sctl_cuda_finalize(void) {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.have_comms) {
+    for (int i = 0; i < g.n_gpus; i++)
+      if (g.comms[i]) g.nccl.CommDestroy(g.comms[i]);
+    memset(g.comms, 0, sizeof(g.comms));
+    g.have_comms = false;
+  }
+  g.n_gpus = 0;
+  return 0;
+}
+
+int sctl_cuda_kernel_info(int kernel_id, int* k0, int* k1, int* nd, int* flops, int* f_alg, double* scale, const char** name) {
+  if (kernel_id < 0 || kernel_id >= NUM_KERNELS) return fail("unknown kernel id %d", kernel_id);
+  const KernelInfo ki = kernel_info(kernel_id);
+  if (k0) *k0 = ki.k0;
+  if (k1) *k1 = ki.k1;
+  if (nd) *nd = ki.nd;
+  if (flops) *flops = ki.flops;
+  if (f_alg) *f_alg = ki.f_alg;
+  if (scale) *scale = scale_factor<double>(kernel_id);
+  if (name) *name = ki.name;
+  return 0;
+}
+
+int sctl_cuda_eval_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* d_r_src, const void* d_n_src, const void* d_v_src,
+                          const void* d_r_trg, void* d_v_trg, void* stream) {
+  if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  int dev;
+  if (current_device_ready(&dev)) return 1;
+  return eval_device_any(dev, kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_v_src, d_r_trg, d_v_trg, (cudaStream_t)stream);
+}
+
+int sctl_cuda_kernel_matrix_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* d_r_src, const void* d_n_src,
+                                   const void* d_r_trg, void* d_M, int64_t ldM, void* stream) {
+  if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  int dev;
+  if (current_device_ready(&dev)) return 1;
+  return kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_r_trg, d_M, ldM, (cudaStream_t)stream);
+}
+
+int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src,
+                   const void* r_trg, void* v_trg, const void* ctx, int64_t ctx_bytes) {
+  (void)ctx;
+  (void)ctx_bytes;
+  if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  const KernelInfo ki = kernel_info(kernel_id);
+  int dev;
+  if (current_device_ready(&dev)) return 1;
+  tl.h2d_ms = tl.kernel_ms = tl.d2h_ms = 0;
+  if (Ns == 0 || Nt == 0) return 0;
+  if (!r_src || !v_src || !r_trg || !v_trg) return fail("null array pointer");
+  if (ki.nd && !n_src) return fail("kernel %s needs source normals (n_src is NULL)", ki.name);
+  int P;
+  bool comms;
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    P = g.n_gpus;
+    comms = g.have_comms;
+  }
+  if (P > 1 && comms && (double)Ns * (double)Nt >= MULTI_GPU_MIN_PAIRS && Nt >= P) {
+    std::lock_guard<std::mutex> mlk(g.multi_mu);
+    std::vector<ShardResult> res(P);
+    std::vector<std::thread> th;
+    for (int p = 0; p < P; p++)
+      th.emplace_back(eval_host_shard, p, P, kernel_id, real_bytes, digits, Ns, Nt, (const char*)r_src, (const char*)n_src, (const char*)v_src,
+                      (const char*)r_trg, (char*)v_trg, &res[p]);
+    for (auto& t : th) t.join();
+    for (int p = 0; p < P; p++) {
+      if (res[p].rc) return fail("GPU %d: %s", p, res[p].err.c_str());
+      tl.h2d_ms = std::max(tl.h2d_ms, res[p].h2d);
+      tl.kernel_ms = std::max(tl.kernel_ms, res[p].ker);
+      tl.d2h_ms = std::max(tl.d2h_ms, res[p].d2h);
+    }
+    return 0;
+  }
+  return eval_host_one(dev, kernel_id, real_bytes, digits, Ns, 0, Nt, (const char*)r_src, (const char*)n_src, (const char*)v_src, (const char*)r_trg,
+                       (char*)v_trg, true);
+}
+
+int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg,
+                            void* M, int64_t ldM) {
+  if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  const KernelInfo ki = kernel_info(kernel_id);
+  int dev;
+  if (current_device_ready(&dev)) return 1;
+  if (Ns == 0 || Nt == 0) return 0;
+  if (!r_src || !r_trg || !M) return fail("null array pointer");
+  if (ki.nd && !n_src) return fail("kernel %s needs source normals (n_src is NULL)", ki.name);
+  const size_t rb = (size_t)real_bytes;
+  const int64_t rows = Ns * ki.k0, cols = Nt * ki.k1;
+  if (ldM < cols) return fail("ldM (%lld) smaller than Nt*K1 (%lld)", (long long)ldM, (long long)cols);
+  cudaStream_t st = tl.stream[dev];
+  DevBuf d_rs, d_ns, d_rt, d_M;
+  if (d_rs.alloc(rb * Ns * 3, st) || d_rt.alloc(rb * Nt * 3, st) || d_M.alloc(rb * rows * cols, st)) return 1;
+  if (ki.nd && d_ns.alloc(rb * Ns * ki.nd, st)) return 1;
+  CU_TRY(cudaMemcpyAsync(d_rs.p, r_src, rb * Ns * 3, cudaMemcpyHostToDevice, st));
+  if (ki.nd) CU_TRY(cudaMemcpyAsync(d_ns.p, n_src, rb * Ns * ki.nd, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg, rb * Nt * 3, cudaMemcpyHostToDevice, st));
+  if (kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_rs.p, d_ns.p, d_rt.p, d_M.p, cols, st)) return 1;
+  CU_TRY(cudaMemcpy2DAsync(M, rb * ldM, d_M.p, rb * cols, rb * cols, rows, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int sctl_cuda_rsqrt_device(int real_bytes, int digits, int64_t n, const void* d_x, void* d_y, void* stream) {
+  if (real_bytes != 8 && real_bytes != 4) return fail("real_bytes must be 8 or 4");
+  int dev;
+  if (current_device_ready(&dev)) return 1;
+  if (n <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
+  if (real_bytes == 8) {
+    switch (rsq_mode_for_digits<double>(digits)) {
+      case RSQ_SEED: rsqrt_test_kernel<double, RSQ_SEED><<<blocks, 256, 0, st>>>(n, (const double*)d_x, (double*)d_y); break;
+      case RSQ_NEWTON: rsqrt_test_kernel<double, RSQ_NEWTON><<<blocks, 256, 0, st>>>(n, (const double*)d_x, (double*)d_y); break;
+      default: rsqrt_test_kernel<double, RSQ_CUBIC><<<blocks, 256, 0, st>>>(n, (const double*)d_x, (double*)d_y); break;
+    }
+  } else {
+    if (rsq_mode_for_digits<float>(digits) == RSQ_SEED) rsqrt_test_kernel<float, RSQ_SEED><<<blocks, 256, 0, st>>>(n, (const float*)d_x, (float*)d_y);
+    else rsqrt_test_kernel<float, RSQ_NEWTON><<<blocks, 256, 0, st>>>(n, (const float*)d_x, (float*)d_y);
+  }
+  CU_TRY(cudaGetLastError());
+  return 0;
+}
+
+int sctl_cuda_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms) {
+  if (h2d_ms) *h2d_ms = tl.h2d_ms;
+  if (kernel_ms) *kernel_ms = tl.kernel_ms;
+  if (d2h_ms) *d2h_ms = tl.d2h_ms;
+  return 0;
+}
+
+int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes, int* ctas_per_sm, int* n_launches, double* wave_eff) {
+  if (grid_x) *grid_x = tl.grid_x;
+  if (grid_y) *grid_y = tl.grid_y;
+  if (threads) *threads = tl.threads;
+  if (smem_bytes) *smem_bytes = tl.smem;
+  if (ctas_per_sm) *ctas_per_sm = tl.ctas_per_sm;
+  if (n_launches) *n_launches = tl.n_launches;
+  if (wave_eff) *wave_eff = tl.wave_eff;
+  return 0;
+}
+
+int sctl_cuda_fma_peak(int real_bytes, double ms, double* tflops) {
+  if (!tflops) return fail("null output pointer");
+  if (visible_devices() < 1) return fail("no CUDA device available");
+  if (real_bytes == 8) return fma_peak_t<double>(ms, tflops);
+  if (real_bytes == 4) return fma_peak_t<float>(ms, tflops);
+  return fail("real_bytes must be 8 or 4");
+}
+
+}  // extern "C"
