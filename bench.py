@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric: FP64 pair-interactions/s of Stokes3D_FxU Eval at Ns = Nt = 2^20.
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one full Eval (all 2^20 targets against all 2^20 sources).
+  value     pairs/s with inputs resident in HBM: per step the timed region is, on every rank, source replication
+            (NCCL broadcasts, N > 1) + source packing + the pair kernel (+ the partial-sum reduce) + the result
+            gather (N > 1); CUDA events on the launching stream, max over ranks, summed over K steps.
+  e2e       the same metric through the host-facing API with HOST (pinned) buffers: H2D of that rank's inputs,
+            the work above, D2H of the result, every step.
+  roofline  the pair kernel against the FP64 CUDA-core peak measured in this run by a DFMA micro-benchmark
+            (MEASURED_PEAKS.json has no FP64 entry); achieved = pairs x F_alg(29 flop) / kernel time.
+  cpu_baseline  the reference's own OpenMP/AVX Eval (oracle/_ref, the unmodified reference compiled by
+            oracle/Makefile; falls back to the C port) on all sources x a strided target subsample, on the box's
+            host cores, rank 0, N = 1 only.  The same call provides the parity figure printed in the line.
+--impl reference times that CPU arm alone on the same workload (bounded sample per step) and prints the same line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "fp64_pair_interactions_per_s"
+UNIT = "pairs/s"
+F_ALG = {"Laplace3D_FxU": 11, "Laplace3D_DxU": 19, "Laplace3D_FxdU": 18, "Stokes3D_FxU": 29, "Stokes3D_DxU": 30}
+DIMS = {"Laplace3D_FxU": (1, 1, 0), "Laplace3D_DxU": (1, 1, 3), "Laplace3D_FxdU": (1, 3, 0), "Stokes3D_FxU": (3, 3, 0), "Stokes3D_DxU": (3, 3, 3)}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # samples under load = upper half (the sampler also sees the gaps between steps)
+        load = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_arm(kernel, N, nsub, steps, warmup, want_result=False):
+    """The reference's CPU Eval on all N sources x nsub strided targets; returns (pairs/s, info, subset result)."""
+    import oracle
+    from sctl_b200 import synth
+    orc = oracle.best_cpu_oracle()
+    k0, k1, nd = DIMS[kernel]
+    r_src, n_src, v_src, r_trg = synth.cube(N, N, k0, nd)
+    idx = np.arange(nsub) * (N // nsub)
+    sub = np.ascontiguousarray(r_trg.reshape(-1, 3)[idx]).reshape(-1)
+    for _ in range(max(warmup, 2)):  # the reference's first calls pay OpenMP start-up and its scratch-pool first touch
+        orc.eval(kernel, r_src, n_src, v_src, sub)
+    times, res = [], None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        res = orc.eval(kernel, r_src, n_src, v_src, sub)
+        times.append(time.perf_counter() - t0)
+    pairs = float(N) * nsub
+    info = {"kind": orc.kind, "cores": orc.threads(), "sample": "all %d sources x %d strided targets (%.3g pairs) per step" % (N, nsub, pairs),
+            "isa": getattr(orc, "isa", "portable-C")}
+    return pairs * steps / sum(times), info, (idx, res) if want_result else None, sum(times) / steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", default="Stokes3D_FxU", choices=list(DIMS))
+    ap.add_argument("--log2n", type=int, default=20, help="Ns = Nt = 2^log2n (BASELINE: 20)")
+    ap.add_argument("--digits", type=int, default=-1)
+    ap.add_argument("--cpu-targets", type=int, default=1 << 14, help="strided target subsample for the CPU baseline / parity")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N = 1 << args.log2n
+    kernel = args.kernel
+    k0, k1, nd = DIMS[kernel]
+    workload = "%s GenericKernel::Eval FP64, Ns=Nt=2^%d uniform in unit cube (BASELINE configs[2])" % (kernel, args.log2n)
+    config = {"workload": workload, "kernel": kernel, "Ns": N, "Nt": N, "digits": args.digits, "inputs": "SplitMix64 streams (SURVEY 8d), f64",
+              "sharding": "targets by contiguous block over %d GPU(s), sources replicated by NCCL broadcast" % args.gpus,
+              "l2": "a 256 MiB buffer is overwritten between timed steps (L2 flush)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        nsub = min(N, 1 << 13)
+        val, info, _, sec = cpu_arm(kernel, N, nsub, args.steps, args.warmup)
+        info["value"] = val
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": config, "cpu_baseline": info, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "note": "reference CPU arm: SCTL's own OpenMP/Vec<> Eval on the host cores, bounded target sample per step"}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import sctl_b200 as sb
+    from sctl_b200 import synth
+    from sctl_b200.sharded import ShardedEval, block_range
+
+    sb.load_library()
+    if not torch.cuda.is_available() or sb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
+
+    # ---- inputs: every rank generates only its own slices (counter-based generator) ----------------------
+    s0, s1 = block_range(N, rank, world)
+    t0, t1 = block_range(N, rank, world)
+    r_src, n_src, v_src, r_trg = synth.cube(s1 - s0, t1 - t0, k0, nd, first_src=s0, first_trg=t0)
+    pin = lambda a: None if a is None else torch.from_numpy(a).pin_memory()
+    h_r_src, h_n_src, h_v_src, h_r_trg = pin(r_src), pin(n_src), pin(v_src), pin(r_trg)
+    h_v_trg = torch.zeros((t1 - t0) * k1, dtype=torch.float64).pin_memory()
+    to_dev = lambda h: None if h is None else h.to(dev, non_blocking=True)
+    d_r_src, d_n_src, d_v_src, d_r_trg = to_dev(h_r_src), to_dev(h_n_src), to_dev(h_v_src), to_dev(h_r_trg)
+    d_v_trg = torch.zeros((t1 - t0) * k1, dtype=torch.float64, device=dev)
+    sh = ShardedEval(kernel, N, N, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    h_out = torch.empty((t1 - t0) * k1, dtype=torch.float64).pin_memory()
+    stream = torch.cuda.current_stream()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        d_v_trg.zero_()
+        v = sh.eval(d_r_src, d_n_src, d_v_src, d_r_trg, v_trg_local=d_v_trg, digits=args.digits)
+        return sh.gather(v) if world > 1 else v
+
+    def step_e2e():
+        a, b, c, d = to_dev(h_r_src), to_dev(h_n_src), to_dev(h_v_src), to_dev(h_r_trg)
+        v = to_dev(h_v_trg)  # Eval accumulates: the caller's v_trg goes up with the inputs
+        v = sh.eval(a, b, c, d, v_trg_local=v, digits=args.digits)
+        h_out.copy_(v, non_blocking=True)
+        stream.synchronize()
+        return h_out
+
+    def timed(fn, steps):
+        per_step = []
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            barrier()
+            ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            per_step.append(float(ms.item()))
+        return per_step
+
+    # ---- peak (roofline denominator) and warm-up -----------------------------------------------------------
+    peak_burst = sb.fma_peak(8, 50.0)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    plan = sb.last_plan()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    res_ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    full = step_resident()  # one more, untimed, to keep the result for the parity figure
+    torch.cuda.synchronize()
+
+    # kernel-only time: pack + pair kernel (+ reduce) on this rank, no collectives
+    ker_ms = []
+    for _ in range(max(2, min(args.steps, 3))):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d_v_trg.zero_()
+        e0.record(stream)
+        sb.eval_device(kernel, sh.r_src, sh.n_src, sh.v_src, d_r_trg, d_v_trg, digits=args.digits)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ker_ms.append(e0.elapsed_time(e1))
+    peak_sustained = sb.fma_peak(8, 1500.0)  # right after the timed region: same thermal / power state
+
+    e2e = None
+    if not args.no_e2e:
+        step_e2e()
+        e2e_ms = timed(step_e2e, args.steps)
+        bi = sum(h.numel() * 8 for h in (h_r_src, h_n_src, h_v_src, h_r_trg, h_v_trg) if h is not None)
+        e2e = {"value": float(N) * N * args.steps / (sum(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi * world, "d2h_bytes_per_step": h_out.numel() * 8 * world,
+               "ms_per_step": sum(e2e_ms) / args.steps, "api": "sctl_b200.sharded.ShardedEval.eval on pinned host buffers (H2D + replicate + Eval + D2H per step)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    pairs = float(N) * N
+    total_s = sum(res_ms) * 1e-3
+    value = pairs * args.steps / total_s
+    my_pairs = float(N) * (t1 - t0)
+    k_ms = float(np.mean(ker_ms))
+    achieved = my_pairs * F_ALG[kernel] / (k_ms * 1e-3) * 1e-12
+    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": None,
+                "peak_source": "DFMA micro-benchmark in this run (sctl_cuda_fma_peak, 1.5 s sustained, FMA = 2 flop); burst 50 ms figure %.2f; MEASURED_PEAKS.json has no FP64 entry" % peak_burst,
+                "kernel": "eval_pairs_kernel<double, %s>" % kernel, "kernel_ms": k_ms, "pairs_per_launch": my_pairs, "flop_per_pair": F_ALG[kernel],
+                "frac_sctl_flops_convention": my_pairs * {"Stokes3D_FxU": 23, "Stokes3D_DxU": 26, "Laplace3D_FxU": 6, "Laplace3D_DxU": 14, "Laplace3D_FxdU": 11}[kernel] / (k_ms * 1e-3) * 1e-12 / peak_sustained,
+                "fp64_instr_per_pair": 22, "pipe_ceiling_frac": F_ALG[kernel] / (2.0 * 22) if kernel == "Stokes3D_FxU" else None}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(res_ms) / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "gpu_launches": int(plan["n_launches"]) * args.steps, "launch_plan": plan, "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+
+    if not args.no_cpu_baseline and world == 1:
+        nsub = min(N, args.cpu_targets)
+        val, info, (idx, cpu_res), _ = cpu_arm(kernel, N, nsub, 2, 2, want_result=True)
+        info.update({"value": val, "unit": UNIT})
+        line["cpu_baseline"] = info
+        got = full.cpu().numpy().reshape(-1, k1)[idx].reshape(-1)
+        line["parity"] = {"max_abs_err_over_vinf": float(np.abs(got - cpu_res).max() / np.abs(full.cpu().numpy()).max()), "gate": 1e-12,
+                          "checked": "%d strided targets x all sources vs the CPU arm above" % nsub}
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -106,6 +106,12 @@ int sctl_cuda_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
 /* Launch geometry the last device-level Eval of the calling thread used (any pointer may be NULL). */
 int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes, int* ctas_per_sm, int* n_launches, double* wave_eff);
 
+/* The grid planner, exposed for host-side tests (no GPU needed): for Nt targets in blocks of `tpb`, Ns sources
+ * and `slots` resident CTAs (SMs x CTAs/SM) returns the number of source chunks, their length and the fraction
+ * of the last wave that does useful work. */
+int sctl_cuda_plan_eval(int64_t Ns, int64_t Nt, int tpb, int slots, int min_chunk, int max_split,
+                        int64_t* n_tblocks, int* n_split, int64_t* chunk, double* wave_eff);
+
 /* FMA-throughput micro-benchmark of the current device: dependent-free DFMA (real_bytes 8) or FFMA (4)
  * chains for about `ms` milliseconds; returns achieved TFLOP/s (FMA = 2 flop) -- the roofline denominator. */
 int sctl_cuda_fma_peak(int real_bytes, double ms, double* tflops);

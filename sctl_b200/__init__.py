@@ -51,6 +51,7 @@ def load_library():
     L.sctl_cuda_last_timing.argtypes = [dp, dp, dp]
     L.sctl_cuda_last_plan.argtypes = [ip, ip, ip, ip, ip, ip, dp]
     L.sctl_cuda_fma_peak.argtypes = [i, C.c_double, dp]
+    L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
     _lib = L
     return L
 
@@ -104,6 +105,13 @@ def last_plan():
     out = {k: x.value for k, x in zip(keys, v)}
     out["wave_eff"] = w.value
     return out
+
+
+def plan_eval(Ns, Nt, tpb, slots, min_chunk, max_split):
+    """The grid planner (csrc/eval_kernel.cuh plan_eval): pure host logic, no GPU needed."""
+    nb, ch, sp, eff = C.c_int64(), C.c_int64(), C.c_int(), C.c_double()
+    _check(load_library().sctl_cuda_plan_eval(Ns, Nt, tpb, slots, min_chunk, max_split, C.byref(nb), C.byref(sp), C.byref(ch), C.byref(eff)))
+    return dict(n_tblocks=nb.value, n_split=sp.value, chunk=ch.value, wave_eff=eff.value)
 
 
 def fma_peak(real_bytes=8, ms=200.0):

@@ -125,7 +125,7 @@ template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAG
   static_assert(R == 1 || (size_t)NW * T * K1 * 32 * sizeof(Real) <= STAGES * STAGE_BYTES, "reduction scratch must fit in the ring");
 };
 
-template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES, int MINB>
+template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES, int MINB, int U = 2>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const EvalArgs<Real> a) {
   using Cfg = EvalConfig<Real, KID, T, NW, R, RSQ, TILE, STAGES>;
   constexpr int REC = Cfg::REC;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const E
     const Real* tile = ring + st * Cfg::STAGE_REALS;
     const int64_t rem = n_src - (int64_t)i * TILE;
     const int n = (int)(rem < TILE ? rem : TILE);
-#pragma unroll 2
+#pragma unroll U
     for (int s = rep; s < n; s += R) {
       Real rec[REC];
       const Vec16* p = reinterpret_cast<const Vec16*>(tile + s * REC);

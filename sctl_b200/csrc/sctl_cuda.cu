@@ -728,6 +728,17 @@ int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes,
   return 0;
 }
 
+int sctl_cuda_plan_eval(int64_t Ns, int64_t Nt, int tpb, int slots, int min_chunk, int max_split, int64_t* n_tblocks, int* n_split, int64_t* chunk,
+                        double* wave_eff) {
+  if (tpb < 1 || slots < 1 || max_split < 1) return fail("bad planner arguments");
+  const EvalPlan p = plan_eval(Ns, Nt, tpb, slots, min_chunk, max_split);
+  if (n_tblocks) *n_tblocks = p.n_tblocks;
+  if (n_split) *n_split = p.n_split;
+  if (chunk) *chunk = p.chunk;
+  if (wave_eff) *wave_eff = p.wave_eff;
+  return 0;
+}
+
 int sctl_cuda_fma_peak(int real_bytes, double ms, double* tflops) {
   if (!tflops) return fail("null output pointer");
   if (visible_devices() < 1) return fail("no CUDA device available");

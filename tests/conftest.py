@@ -1,0 +1,64 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+# north_star tolerances: max|dv| / ||v||_inf
+TOL = {np.float64: 1e-12, np.float32: 1e-5}
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64).reshape(-1)
+    b = np.asarray(b, dtype=np.float64).reshape(-1)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    den = np.abs(b).max()
+    return float(np.abs(a - b).max() / (den if den > 0 else 1.0))
+
+
+@pytest.fixture(scope="session")
+def port():
+    import oracle
+    return oracle.PortOracle()
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference (oracle/_ref); skipped where it was never built."""
+    import oracle
+    try:
+        return oracle.RefOracle()
+    except (FileNotFoundError, OSError) as e:
+        pytest.skip("oracle/_ref not built: %s" % e)
+
+
+@pytest.fixture(scope="session")
+def cpu_oracle():
+    import oracle
+    return oracle.best_cpu_oracle()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_eval.npz"))
+
+
+@pytest.fixture(scope="session")
+def sb():
+    """The product package with the CUDA library loaded and a device present (gpu tests only)."""
+    import sctl_b200
+    sctl_b200.load_library()
+    if sctl_b200.device_count() < 1:
+        pytest.fail("gpu test selected but no CUDA device is visible (the product has no CPU fallback)")
+    return sctl_b200

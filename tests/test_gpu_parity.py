@@ -1,0 +1,264 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI, against the golden
+vectors of the unmodified reference and against the CPU oracle on the same seeded inputs.
+Tolerances are north_star's: max|dv|/||v||_inf <= 1e-12 (FP64), <= 1e-5 (FP32)."""
+import threading
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+KERNELS = list(cases.KERNELS)
+DTYPES = [np.float64, np.float32]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_eval_matches_reference_golden(sb, golden, kernel, dtype):
+    K = sb.KERNELS[kernel]
+    for Ns, Nt, variant, digits in cases.EVAL_CASES:
+        r_src, n_src, v_src, r_trg, v0 = cases.inputs(kernel, Ns, Nt, variant, dtype)
+        got = K.Eval(None if v0 is None else v0.copy(), r_trg, r_src, n_src, v_src, digits=digits, dtype=dtype)
+        want = golden[cases.key(kernel, dtype, Ns, Nt, variant, digits)]
+        assert got.dtype == want.dtype and got.shape == want.shape
+        assert np.all(np.isfinite(got)), (kernel, Ns, Nt, variant)
+        assert rel_err(got, want) <= TOL[dtype], (kernel, dtype.__name__, Ns, Nt, variant, digits, rel_err(got, want))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_kernel_matrix_matches_reference_golden(sb, golden, kernel, dtype):
+    K = sb.KERNELS[kernel]
+    for Ns, Nt in cases.KMAT_CASES:
+        r_src, n_src, _, r_trg, _ = cases.inputs(kernel, Ns, Nt, "cube", dtype)
+        got = K.KernelMatrix(r_trg, r_src, n_src, dtype=dtype)
+        want = golden[cases.kmat_key(kernel, dtype, Ns, Nt)]
+        assert got.shape == want.shape == (Ns * K.SrcDim(), Nt * K.TrgDim())
+        assert rel_err(got, want) <= TOL[dtype] * (10 if dtype == np.float32 else 1), (kernel, Ns, Nt, rel_err(got, want))
+
+
+# Shapes chosen around the kernel's internal boundaries: 32*T target groups, the few-target threshold (2048),
+# the 512-target CTA, tile lengths 256/512 and chunk splits; plus ragged and degenerate sizes.
+SHAPES = [(1, 1), (2, 31), (255, 32), (256, 33), (257, 511), (513, 512), (1023, 513), (4097, 2047), (4099, 2048), (3001, 2049),
+          (16384, 4100), (777, 10000), (40000, 300), (5, 20000)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_eval_matches_oracle_over_shapes(sb, cpu_oracle, kernel, dtype):
+    K = sb.KERNELS[kernel]
+    k0, k1, nd = cases.KERNELS[kernel]
+    from sctl_b200 import synth
+    for Ns, Nt in SHAPES:
+        r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
+        got = K.Eval(None, r_trg, r_src, n_src, v_src, dtype=dtype)
+        want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg, dtype=dtype)
+        assert got.shape == (Nt * k1,)
+        assert rel_err(got, want) <= TOL[dtype], (kernel, dtype.__name__, Ns, Nt, rel_err(got, want), sb.last_plan())
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_empty_inputs(sb, kernel):
+    K = sb.KERNELS[kernel]
+    k0, k1, nd = cases.KERNELS[kernel]
+    e = np.zeros(0)
+    # no sources: result is all zeros of the right size; existing contents are kept
+    out = K.Eval(None, np.arange(6.0), e, e if nd else None, e)
+    assert out.shape == (2 * k1,) and np.all(out == 0)
+    pre = np.arange(2.0 * k1)
+    out = K.Eval(pre.copy(), np.arange(6.0), e, e if nd else None, e)
+    assert np.array_equal(out, pre)
+    # no targets: empty result
+    out = K.Eval(None, e, np.arange(3.0), np.ones(3) if nd else None, np.ones(k0))
+    assert out.shape == (0,)
+    M = K.KernelMatrix(e, np.arange(3.0), np.ones(3) if nd else None)
+    assert M.shape == (k0, 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_accumulate_and_resize_semantics(sb, cpu_oracle, dtype):
+    # generic-kernel.txx:129-132,206: accumulate into a right-sized v_trg, reset a wrong-sized one
+    from sctl_b200 import synth
+    K = sb.Stokes3D_FxU
+    r_src, n_src, v_src, r_trg = synth.cube(700, 300, 3, 0, dtype=dtype)
+    once = K.Eval(None, r_trg, r_src, None, v_src, dtype=dtype)
+    pre = (synth.splitmix_u01(11, 900) - 0.5).astype(dtype)
+    acc = K.Eval(pre.copy(), r_trg, r_src, None, v_src, dtype=dtype)
+    assert rel_err(acc, (pre.astype(np.float64) + once.astype(np.float64))) <= TOL[dtype]
+    twice = K.Eval(once.copy(), r_trg, r_src, None, v_src, dtype=dtype)
+    assert rel_err(twice, 2 * once.astype(np.float64)) <= TOL[dtype]
+    wrong = K.Eval(np.full(17, 5.0, dtype=dtype), r_trg, r_src, None, v_src, dtype=dtype)
+    assert np.array_equal(wrong, once)
+    # a non-empty normal vector is tolerated and ignored by single-layer kernels (:128)
+    ign = K.Eval(None, r_trg, r_src, np.ones(2100, dtype=dtype), v_src, dtype=dtype)
+    assert np.array_equal(ign, once)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_self_interaction_is_masked(sb, cpu_oracle, kernel, dtype):
+    # targets == sources: every target has one r2 == 0 pair that must contribute exactly 0 (kernel_functions.hpp:45)
+    from sctl_b200 import synth
+    K = sb.KERNELS[kernel]
+    k0, k1, nd = cases.KERNELS[kernel]
+    N = 3000
+    r_src, n_src, v_src, _ = synth.cube(N, 0, k0, nd, dtype=dtype)
+    got = K.Eval(None, r_src, r_src, n_src, v_src, dtype=dtype)
+    want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_src, dtype=dtype)
+    assert np.all(np.isfinite(got))
+    assert rel_err(got, want) <= TOL[dtype]
+    # one source exactly on one target, far from everything else: the result is exactly 0
+    out = K.Eval(None, np.array([0.3, 0.2, 0.1], dtype=dtype), np.array([0.3, 0.2, 0.1], dtype=dtype), np.ones(3, dtype=dtype) if nd else None, np.ones(k0, dtype=dtype))
+    assert np.all(out == 0)
+    M = K.KernelMatrix(np.array([0.3, 0.2, 0.1], dtype=dtype), np.array([0.3, 0.2, 0.1], dtype=dtype), np.ones(3, dtype=dtype) if nd else None, dtype=dtype)
+    assert np.all(M == 0)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_digits_classes(sb, cpu_oracle, kernel):
+    # accuracy at least `digits` decimal digits, like approx_rsqrt<digits> (vec.txx:375-382); 10 and 11 are what
+    # ParticleFMM / BoundaryIntegralOp pass (fmm-wrapper.txx:205, boundary_integral.txx:562)
+    from sctl_b200 import synth
+    K = sb.KERNELS[kernel]
+    k0, k1, nd = cases.KERNELS[kernel]
+    r_src, n_src, v_src, r_trg = synth.cube(2000, 1000, k0, nd)
+    v_src = np.abs(v_src)  # one-signed densities: no cancellation, so the sum's relative error tracks the per-pair error
+    if nd:
+        n_src = np.abs(n_src)
+        r_trg = r_trg + 1.5  # targets on one side of every source: (r.n) > 0
+    want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg)
+    for digits in (0, 3, 5, 6, 8, 10, 11, 12, 15, 16, -1):
+        got = K.Eval(None, r_trg, r_src, n_src, v_src, digits=digits)
+        d = 15 if digits in (-1, 16) else digits
+        bound = max(6 * 10.0 ** -d, 1e-12)  # rinv enters up to the 5th power
+        assert rel_err(got, want) <= bound, (kernel, digits, rel_err(got, want))
+    r32 = [a if a is None else a.astype(np.float32) for a in (r_src, n_src, v_src, r_trg)]
+    want32 = cpu_oracle.eval(kernel, r32[0], r32[1], r32[2], r32[3], dtype=np.float32)
+    for digits in (0, 4, 6, 7, -1):
+        got = K.Eval(None, r32[3], r32[0], r32[1], r32[2], digits=digits, dtype=np.float32)
+        assert rel_err(got, want32) <= 1e-5, (kernel, digits, rel_err(got, want32))
+
+
+def test_rsqrt_contract_on_device(sb):
+    # vec-test.hpp:431-465: approx_rsqrt<4> < 2^-11, <7> < 2^-22, masked lanes exactly 0 -- plus every digits class
+    import torch
+    x = np.concatenate([10.0 ** np.linspace(-300, 300, 20001), [0.0, np.inf, np.nan, -1.0, 5e-324, 1e-310]])
+    exact = 1 / np.sqrt(x[:20001])
+    dx = torch.from_numpy(x).cuda()
+    for digits in (0, 4, 5, 7, 10, 11, 12, 15, -1):
+        dy = torch.empty_like(dx)
+        sb.rsqrt_device(dx, dy, digits=digits)
+        y = dy.cpu().numpy()
+        d = 15 if digits == -1 else digits
+        bound = {4: 2.0 ** -11, 7: 2.0 ** -22}.get(digits, max(10.0 ** -d, 3e-16))
+        err = np.abs(y[:20001] - exact) / exact
+        assert err.max() < bound, (digits, err.max())
+        assert np.all(y[20001:] == 0), y[20001:]  # zero, Inf, NaN, negative and subnormal inputs are masked to 0
+    xf = np.concatenate([10.0 ** np.linspace(-37, 38, 20001), [0.0, np.inf, np.nan, -1.0, 1e-45, 1e-39]]).astype(np.float32)
+    exf = 1 / np.sqrt(xf[:20001].astype(np.float64))
+    dxf = torch.from_numpy(xf).cuda()
+    for digits, bound in ((4, 2.0 ** -11), (6, 1e-6), (-1, 1e-6), (7, 2.0 ** -22)):
+        dyf = torch.empty_like(dxf)
+        sb.rsqrt_device(dxf, dyf, digits=digits)
+        y = dyf.cpu().numpy().astype(np.float64)
+        assert (np.abs(y[:20001] - exf) / exf).max() < bound, (digits, (np.abs(y[:20001] - exf) / exf).max())
+        assert np.all(y[20001:] == 0)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_device_path_unaligned_views_and_streams(sb, cpu_oracle, dtype):
+    """sctl_cuda_eval_device on torch tensors that are NOT 16-byte aligned, on a side stream, in place."""
+    import torch
+    from sctl_b200 import synth
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    for kernel in ("Stokes3D_DxU", "Laplace3D_FxU"):
+        k0, k1, nd = cases.KERNELS[kernel]
+        Ns, Nt = 5001, 4099
+        r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
+
+        def odd(a):  # a view starting one element into a fresh allocation: 8- or 4-byte aligned only
+            buf = torch.empty(a.size + 1, dtype=tdt, device="cuda")
+            buf[1:].copy_(torch.from_numpy(a))
+            return buf[1:]
+
+        d = [odd(r_src), odd(n_src) if nd else None, odd(v_src), odd(r_trg)]
+        pre = (synth.splitmix_u01(5, Nt * k1) - 0.5).astype(dtype)
+        d_v = odd(pre)
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_v)
+        st.synchronize()
+        want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg, v_trg=pre, dtype=dtype)
+        assert rel_err(d_v.cpu().numpy(), want) <= TOL[dtype]
+        assert sb.last_plan()["n_launches"] >= 2  # pack + pair kernel (+ reduce): our kernels ran
+        # KernelMatrix on device, with a padded leading dimension
+        Nsm, Ntm = 37, 53
+        ld = Ntm * k1 + 3
+        dM = torch.full((Nsm * k0, ld), -7.0, dtype=tdt, device="cuda")
+        sb.kernel_matrix_device(kernel, d[0][: Nsm * 3], None if d[1] is None else d[1][: Nsm * 3], d[3][: Ntm * 3], dM, ldM=ld)
+        torch.cuda.synchronize()
+        Mh = dM.cpu().numpy()
+        wantM = cpu_oracle.kernel_matrix(kernel, r_src[: Nsm * 3], None if n_src is None else n_src[: Nsm * 3], r_trg[: Ntm * 3], dtype=dtype)
+        assert rel_err(Mh[:, : Ntm * k1], wantM) <= TOL[dtype] * (10 if dtype == np.float32 else 1)
+        assert np.all(Mh[:, Ntm * k1:] == -7.0)  # padding columns untouched
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_eval_equals_kernel_matrix_apply_and_linearity(sb, kernel):
+    from sctl_b200 import synth
+    K = sb.KERNELS[kernel]
+    k0, k1, nd = cases.KERNELS[kernel]
+    Ns, Nt = 300, 200
+    r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd)
+    v = K.Eval(None, r_trg, r_src, n_src, v_src)
+    M = K.KernelMatrix(r_trg, r_src, n_src)
+    assert rel_err(v, M.T @ v_src) <= 1e-12  # test-kernel_functions.cpp:488-526 at a larger size
+    g = synth.splitmix_u01(21, Ns * k0) - 0.5
+    va, vb = K.Eval(None, r_trg, r_src, n_src, g), K.Eval(None, r_trg, r_src, n_src, 2.0 * v_src - 3.0 * g)
+    assert rel_err(vb, 2.0 * v - 3.0 * va) <= 1e-12
+
+
+def test_deterministic_and_split_invariant(sb):
+    """Same inputs -> bit-identical outputs (no atomics), also when the planner splits the source range."""
+    from sctl_b200 import synth
+    K = sb.Stokes3D_FxU
+    r_src, _, v_src, r_trg = synth.cube(60000, 3000, 3, 0)
+    a = K.Eval(None, r_trg, r_src, None, v_src)
+    assert sb.last_plan()["grid_y"] > 1  # this shape is evaluated with source chunks + the reduce kernel
+    b = K.Eval(None, r_trg, r_src, None, v_src)
+    assert np.array_equal(a, b)
+
+
+def test_concurrent_host_threads(sb, cpu_oracle):
+    """The C ABI is re-entrant: KernelMatrix<Real,false> is called from OpenMP threads in the reference
+    (boundary_integral.txx:1169-1211)."""
+    from sctl_b200 import synth
+    K = sb.Laplace3D_DxU
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            r_src, n_src, v_src, r_trg = synth.cube(64 + i, 50 + 3 * i, 1, 3, first_src=100 * i, first_trg=77 * i)
+            results[i] = (K.KernelMatrix(r_trg, r_src, n_src), K.Eval(None, r_trg, r_src, n_src, v_src), r_src, n_src, v_src, r_trg)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    for i, (M, v, r_src, n_src, v_src, r_trg) in results.items():
+        assert rel_err(M, cpu_oracle.kernel_matrix("Laplace3D_DxU", r_src, n_src, r_trg)) <= 1e-12
+        assert rel_err(v, cpu_oracle.eval("Laplace3D_DxU", r_src, n_src, v_src, r_trg)) <= 1e-12
+
+
+def test_config1_laplace_fxu_20k(sb, cpu_oracle):
+    """BASELINE config 1 in full: Laplace3D_FxU FP64, 20k sources x 20k targets in the unit cube."""
+    from sctl_b200 import synth
+    r_src, _, v_src, r_trg = synth.cube(20000, 20000, 1, 0)
+    got = sb.Laplace3D_FxU.Eval(None, r_trg, r_src, None, v_src)
+    want = cpu_oracle.eval("Laplace3D_FxU", r_src, None, v_src, r_trg)
+    assert rel_err(got, want) <= 1e-12

@@ -1,0 +1,116 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/sctl_cuda.h declares, reports the
+reference's kernel metadata, plans grids sanely, and FAILS LOUDLY (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def sbm():
+    import sctl_b200
+    sctl_b200.load_library()
+    return sctl_b200
+
+
+def test_library_exports_every_declared_symbol(sbm):
+    header = open(sbm.HEADER_PATH).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(sctl_cuda_\w+)\s*\(", header)))
+    assert len(declared) >= 14, declared
+    lib = ctypes.CDLL(sbm.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libsctl_cuda.so does not export %s" % name
+    # signatures use plain C types only: no torch / C++ types in the header
+    assert "torch" not in header and "std::" not in header and "at::" not in header
+
+
+def test_product_does_not_link_or_import_the_oracle(sbm):
+    out = subprocess.run(["ldd", sbm.LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "sctl_ref" not in out
+    for root, _, files in os.walk(os.path.join(ROOT, "sctl_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle", src, flags=re.M), f
+                assert "liboracle" not in src and "sctl_ref" not in src, f
+    for f in os.listdir(os.path.join(ROOT, "include", "sctl_cuda")) + ["../sctl_cuda.h"]:
+        src = open(os.path.join(ROOT, "include", "sctl_cuda", f)).read()
+        assert "oracle" not in src.lower(), f
+
+
+def test_kernel_info_matches_oracle_and_python_mirror(sbm, port):
+    for kernel in cases.KERNELS:
+        info, d = sbm.kernel_info(kernel), port.dims(kernel)
+        assert (info["k0"], info["k1"], info["nd"], info["flops"], info["name"]) == (d["k0"], d["k1"], d["nd"], d["flops"], d["name"])
+        assert info["scale"] == d["scale64"]
+        K = sbm.KERNELS[kernel]
+        assert (K.SrcDim(), K.TrgDim(), K.NormalDim(), K.CoordDim(), K.FLOPS(), K.Name()) == (d["k0"], d["k1"], d["nd"], 3, d["flops"], d["name"])
+        assert abs(K.uKerScaleFactor(np.float64) - d["scale64"]) < 1e-16
+        assert abs(float(K.uKerScaleFactor(np.float32)) - d["scale32"]) < 1e-7
+    assert sbm.kernel_info(3)["f_alg"] == 29  # Stokes3D_FxU algorithmic flop per pair
+    with pytest.raises(sbm.SctlCudaError):
+        sbm.kernel_info(7)
+
+
+def test_planner_fills_waves(sbm):
+    slots, tpb = 148 * 2, 512
+    p = sbm.plan_eval(1 << 20, 1 << 20, tpb, slots, 2048, 64)
+    assert p["n_tblocks"] == 2048 and p["n_split"] == 1 and p["wave_eff"] > 0.97
+    p = sbm.plan_eval(1 << 20, 1 << 17, tpb, slots, 2048, 64)  # the 8-GPU shard of the headline config
+    assert p["n_split"] > 1 and p["wave_eff"] > 0.97
+    assert p["n_split"] * p["chunk"] >= (1 << 20) and (p["n_split"] - 1) * p["chunk"] < (1 << 20)
+    for Ns, Nt in ((1, 1), (5, 100000), (100000, 5), (20000, 20000), (3, 1 << 22)):
+        p = sbm.plan_eval(Ns, Nt, tpb, slots, 2048, 64)
+        assert p["n_tblocks"] == -(-Nt // tpb) and 1 <= p["n_split"] <= 64
+        assert p["n_split"] * p["chunk"] >= Ns and (p["n_split"] - 1) * p["chunk"] < Ns  # chunks tile the sources, none empty
+
+
+def test_compute_fails_loudly_without_gpu(sbm):
+    if sbm.device_count() > 0:
+        pytest.skip("a GPU is present")
+    K = sbm.Laplace3D_FxU
+    with pytest.raises(sbm.SctlCudaError, match="no CUDA device"):
+        K.Eval(None, [1.0, 0, 0], [0.0, 0, 0], None, [1.0])
+    with pytest.raises(sbm.SctlCudaError, match="no CUDA device"):
+        K.KernelMatrix([1.0, 0, 0], [0.0, 0, 0], None)
+    with pytest.raises(sbm.SctlCudaError):
+        sbm.init(1)
+    with pytest.raises(sbm.SctlCudaError):
+        sbm.fma_peak(8, 1.0)
+
+
+def test_precondition_violations_raise(sbm):
+    K = sbm.Stokes3D_DxU
+    with pytest.raises(sbm.SctlCudaError, match="v_src"):
+        K.Eval(None, np.zeros(3), np.zeros(6), np.zeros(6), np.zeros(5))  # v_src.Dim() != Ns*KDIM0
+    with pytest.raises(sbm.SctlCudaError, match="n_src"):
+        K.Eval(None, np.zeros(3), np.zeros(6), np.zeros(3), np.zeros(6))  # n_src.Dim() != Ns*N_DIM
+    with pytest.raises(sbm.SctlCudaError, match="r_src"):
+        sbm.Laplace3D_FxU.Eval(None, np.zeros(3), np.zeros(4), None, np.zeros(1))
+    L = sbm.load_library()
+    z = np.zeros(8)
+    p = z.ctypes.data_as(ctypes.c_void_p)
+    assert L.sctl_cuda_eval(9, 8, -1, 1, 1, p, p, p, p, p, None, 0) != 0 and b"kernel id" in L.sctl_cuda_last_error()
+    assert L.sctl_cuda_eval(0, 2, -1, 1, 1, p, p, p, p, p, None, 0) != 0 and b"real_bytes" in L.sctl_cuda_last_error()
+    assert L.sctl_cuda_eval(0, 8, -1, -1, 1, p, p, p, p, p, None, 0) != 0 and b"negative" in L.sctl_cuda_last_error()
+
+
+def test_cpp_host_layer_compiles_standalone(tmp_path):
+    """include/sctl_cuda/*.hpp is self-contained C++17 (no SCTL, no CUDA headers needed by callers)."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "sctl_cuda/generic_kernel.hpp"\n#include "sctl_cuda/mini_containers.hpp"\n'
+                   "int main(){ sctl_cuda::Stokes3D_FxU K; static_assert(decltype(K)::SrcDim()==3 && decltype(K)::TrgDim()==3 && decltype(K)::NormalDim()==0, \"dims\");\n"
+                   " return (K.Name()==\"Stokes3D-FxU\" && K.FLOPS()==23) ? 0 : 1; }\n")
+    exe = tmp_path / "t"
+    r = subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", os.path.join(ROOT, "sctl_b200"), "-lsctl_cuda", "-Wl,-rpath," + os.path.join(ROOT, "sctl_b200")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0
