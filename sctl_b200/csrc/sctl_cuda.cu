@@ -134,12 +134,16 @@ int visible_devices() {
 // ---------------------------------------------------------------------------------------------
 // digits -> refinement of the reciprocal-square-root seed  (approx_rsqrt<digits>, vec.txx:375-382)
 // ---------------------------------------------------------------------------------------------
-// FP64: seed (MUFU.RSQ64H) is good to ~2^-20 -> 5 digits; one Newton step ~1.4e-12 -> 11 digits; the cubic
-// step is correct to < 1 ulp.  FP32: MUFU.RSQ is good to 2^-22 -> 6 digits; one Newton step -> 7.
+// The classes follow the reference's AVX-512 Newton-count table (intrin-wrapper.hpp:3384, SURVEY appendix A:
+// digits 0-4 -> 0 iterations, 5-8 -> 1, 9-16 -> 2) and are at least as accurate in every class:
+//   FP64: digits <= 5  seed only (MUFU.RSQ64H, ~2^-20 > 5 digits); 6-8 one Newton step (~1e-12);
+//         >= 9 the cubic step (< 1 ulp) -- so digits 10/11 (ParticleFMM / BoundaryIntegralOp) match digits -1,
+//         exactly as they do in the reference on AVX-512.
+//   FP32: digits <= 6 seed only (MUFU.RSQ, 2^-22); 7 and up one Newton step.
 template <class Real> int rsq_mode_for_digits(int digits) {
   if (sizeof(Real) == 8) {
     if (digits < 0 || digits >= 16) digits = 15;  // (Integer)(52*0.30103)
-    return digits <= 5 ? RSQ_SEED : digits <= 11 ? RSQ_NEWTON : RSQ_CUBIC;
+    return digits <= 5 ? RSQ_SEED : digits <= 8 ? RSQ_NEWTON : RSQ_CUBIC;
   } else {
     if (digits < 0 || digits >= 16) digits = 6;  // (Integer)(23*0.30103)
     return digits <= 6 ? RSQ_SEED : RSQ_NEWTON;
