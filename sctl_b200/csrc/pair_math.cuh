@@ -26,8 +26,8 @@ enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
 // FP64.  Seed = MUFU.RSQ64H on the high word (one XU-pipe instruction, valid over the whole normal
 // double range, ~2^-20 relative error because the low mantissa word is ignored).  Refinement runs on
 // the FP64 pipe with the residual e = 1 - x*y0^2:
-//   RSQ_NEWTON: y = y0 + (y0*e)*(1/2)                 4 FP64 instr, error ~ 3/8 e^2  (~1e-12)
-//   RSQ_CUBIC : y = y0 + (y0*e)*(1/2 + 3/8 e)         5 FP64 instr, error ~ 5/16 e^3 (< 1 ulp)
+//   RSQ_NEWTON: y = y0 * (1 + e/2)                    4 FP64 instr, error ~ 3/8 e^2  (~1e-12)
+//   RSQ_CUBIC : y = y0 * (1 + e*(1/2 + 3/8 e))        5 FP64 instr, error ~ 5/16 e^3 (~1 ulp)
 // SCTL's AVX-512 recipe (14-bit seed, 2 Newton steps, deferred scaling) costs 7.
 // Mask: like _mm512_maskz_rsqrt14_pd in the reference (intrin-wrapper.hpp:3403) the SEED is zeroed and the
 // refinement then keeps it zero (e = 1, y0*e = 0).  The test is one integer range check on the high word
@@ -41,9 +41,10 @@ template <int MODE> __device__ __forceinline__ double rsqrt_masked(double x) {
   y0 = __hiloint2double(ok ? __double2hiint(y0) : 0, 0);
   if (MODE == RSQ_SEED) return y0;
   const double e = fma(-x, y0 * y0, 1.0);
-  const double ye = y0 * e;
-  if (MODE == RSQ_NEWTON) return fma(ye, 0.5, y0);
-  return fma(fma(e, 0.375, 0.5), ye, y0);
+  // Written as y0 * (1 + e*p) rather than y0 + (y0*e)*p: every instruction then reads at most two distinct
+  // vector registers.  A DFMA with three distinct register sources issues every 3 cycles instead of 2 on B200.
+  if (MODE == RSQ_NEWTON) return y0 * fma(e, 0.5, 1.0);
+  return y0 * fma(e, fma(e, 0.375, 0.5), 1.0);
 }
 
 // FP32.  Seed = MUFU.RSQ (2^-22 relative error): that already meets approx_rsqrt<digits<=6>, which is what the

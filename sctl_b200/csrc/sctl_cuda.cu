@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/sctl_cuda.h"
+#include "eval_const_kernel.cuh"
 #include "eval_kernel.cuh"
 #include "kmat_kernel.cuh"
 
@@ -65,6 +66,10 @@ thread_local ThreadState tl;
 struct DeviceInfo {
   int sms = 0;
   bool pool_configured = false;
+  // The constant bank that the chunk-streaming kernel reads is one buffer per device: calls that use it are
+  // enqueued under this mutex and chained on the GPU through `const_done`, whatever stream they run on.
+  std::mutex const_mu;
+  cudaEvent_t const_done = nullptr;
 };
 
 struct NcclApi {
@@ -154,14 +159,17 @@ template <class Real> int rsq_mode_for_digits(int digits) {
 // launch configurations
 // ---------------------------------------------------------------------------------------------
 // MAIN: many targets.  FEW: few targets -- all warps of a CTA share 32*T targets and split the sources.
+// CONST: very many targets -- sources streamed through the constant bank into uniform registers (eval_const_kernel.cuh).
 template <class Real> struct Tune;
 template <> struct Tune<double> {
   static constexpr int T = 2, NW = 8, TILE = 256, STAGES = 3, MINB = 2;
   static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 256, FEW_STAGES = 3, FEW_MINB = 2;
+  static constexpr int CONST_T = 2, CONST_NT = 256, CONST_U = 4, CONST_MINB = 2;
 };
 template <> struct Tune<float> {
   static constexpr int T = 4, NW = 8, TILE = 512, STAGES = 3, MINB = 2;
   static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 512, FEW_STAGES = 3, FEW_MINB = 2;
+  static constexpr int CONST_T = 4, CONST_NT = 128, CONST_U = 2, CONST_MINB = 4;
 };
 
 struct OccCache {
@@ -224,6 +232,63 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
   return 0;
 }
 
+// Chunk-streaming path: for every CONST_PACK_BYTES of packed sources, copy them into the constant bank (device to
+// device, stream ordered) and launch eval_pairs_const_kernel over all targets.  Each launch costs a fixed ~20 us
+// (kernel boundary + cold constant cache), so the path is used only when a chunk x Nt is >= ~2 ms of work.
+constexpr int64_t CONST_MIN_TARGETS = 1 << 18;
+
+template <class Real, int KID, int RSQ>
+int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
+  using Tn = Tune<Real>;
+  constexpr int T = Tn::CONST_T, NT = Tn::CONST_NT;
+  constexpr int REC = RecTraits<Real, KID>::REC;
+  constexpr int CH = const_chunk_records<Real, KID>();
+  auto kern = eval_pairs_const_kernel<Real, KID, T, NT, RSQ, Tn::CONST_U, Tn::CONST_MINB>;
+  const int64_t n_tb = (Nt + NT * T - 1) / (NT * T);
+  if (n_tb > 2147483647LL) return fail("too many target blocks");
+  int cl = 1;
+  while (cl < 8 && n_tb * cl < 6 * (int64_t)g.dev[dev].sms) cl *= 2;  // >= 6 CTAs per SM keeps the SMs balanced
+  ConstEvalArgs<Real> a;
+  a.r_trg = r_trg;
+  a.v_trg = v_trg;
+  a.Nt = Nt;
+  a.scale = scale_factor<Real>(KID);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)n_tb, (unsigned)cl);
+  cfg.blockDim = dim3(NT);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = (unsigned)cl;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cl > 1 ? 1 : 0;
+
+  DeviceInfo& di = g.dev[dev];
+  std::lock_guard<std::mutex> lk(di.const_mu);
+  if (!di.const_done) CU_TRY(cudaEventCreateWithFlags(&di.const_done, cudaEventDisableTiming));
+  else CU_TRY(cudaStreamWaitEvent(stream, di.const_done, 0));  // the previous user of the constant bank, on any stream
+  int launches = 0;
+  for (int64_t s0 = 0; s0 < Ns; s0 += CH) {
+    const int n = (int)std::min<int64_t>(CH, Ns - s0);
+    CU_TRY(cudaMemcpyToSymbolAsync(c_src_pack, pack + s0 * REC, sizeof(Real) * (size_t)n * REC, 0, cudaMemcpyDeviceToDevice, stream));
+    a.n_rec = n;
+    a.sub_len = (n + cl - 1) / cl;
+    CU_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+    launches++;
+  }
+  CU_TRY(cudaEventRecord(di.const_done, stream));
+  tl.grid_x = (int)n_tb;
+  tl.grid_y = cl;
+  tl.threads = NT;
+  tl.smem = (int)(sizeof(Real) * T * KerTraits<KID>::K1 * NT);
+  tl.ctas_per_sm = 0;
+  tl.n_launches = launches;
+  tl.wave_eff = 0;
+  return 0;
+}
+
 // few-target threshold: below this many targets the MAIN grid cannot fill the GPU even with source splitting
 constexpr int64_t FEW_TARGETS = 2048;
 
@@ -239,7 +304,9 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
     CU_TRY(cudaGetLastError());
   }
   int rc;
-  if (Nt <= FEW_TARGETS)
+  if (Nt >= CONST_MIN_TARGETS)
+    rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, stream);
+  else if (Nt <= FEW_TARGETS)
     rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, Tn::FEW_TILE, 1024);
   else
     rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, 8 * Tn::TILE, 64);

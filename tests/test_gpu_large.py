@@ -69,6 +69,68 @@ def test_config4_kernels_fp32_fp64_large(sb, cpu_oracle, kernel):
     assert e_gpu <= max(1e-5, 2 * e_cpu), (kernel, e_gpu, e_cpu)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", list(cases.KERNELS))
+def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
+    """Nt >= 2^18 takes the chunk-streaming path (sources through the constant bank into uniform registers, one launch
+    per chunk, 2-CTA clusters at this size): several chunks, ragged last chunk, pre-filled v_trg, every kernel."""
+    import torch
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    Nt, Ns = (1 << 18) + 77, 4500
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
+    pre = (synth.splitmix_u01(13, Nt * k1) - 0.5).astype(dtype)
+    d = [None if a is None else torch.from_numpy(a).cuda() for a in (r_src, n_src, v_src, r_trg)]
+    d_v = torch.from_numpy(pre).cuda()
+    sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_v)
+    torch.cuda.synchronize()
+    plan = sb.last_plan()
+    assert plan["grid_y"] == 2 and plan["n_launches"] >= 3, plan  # pack + one launch per chunk, cluster of 2
+    got = d_v.cpu().numpy().reshape(-1, k1)
+    idx = np.concatenate([np.arange(300) * (Nt // 300), [Nt - 1, Nt - 2, 1 << 17]])
+    want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg.reshape(-1, 3)[idx].reshape(-1), v_trg=pre.reshape(-1, k1)[idx].reshape(-1), dtype=dtype)
+    tol = 1e-12 if dtype == np.float64 else 1e-5
+    assert rel_err(got[idx].reshape(-1), want) <= tol, (kernel, rel_err(got[idx].reshape(-1), want))
+    # same inputs again: bit-identical (no atomics anywhere)
+    d_w = torch.from_numpy(pre).cuda()
+    sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_w)
+    torch.cuda.synchronize()
+    assert torch.equal(d_v, d_w)
+
+
+def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
+    """Two host threads on two streams share the one constant bank: calls must serialise on the GPU, not corrupt each other."""
+    import threading
+
+    import torch
+    from sctl_b200 import synth
+    Nt, Ns = 1 << 18, 3000
+    res = {}
+
+    def work(i):
+        torch.cuda.set_device(0)
+        r_src, _, v_src, r_trg = synth.cube(Ns, Nt, 3, 0, first_src=1000 * i, first_trg=5000 * i)
+        st = torch.cuda.Stream()
+        with torch.cuda.stream(st):
+            d = [torch.from_numpy(a).cuda() for a in (r_src, v_src, r_trg)]
+            d_v = torch.zeros(Nt * 3, dtype=torch.float64, device="cuda")
+            for _ in range(3):
+                d_v.zero_()
+                sb.eval_device("Stokes3D_FxU", d[0], None, d[1], d[2], d_v)
+        st.synchronize()
+        res[i] = (d_v.cpu().numpy(), r_src, v_src, r_trg)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(2):
+        v, r_src, v_src, r_trg = res[i]
+        idx = np.arange(100) * (Nt // 100)
+        want = cpu_oracle.eval("Stokes3D_FxU", r_src, None, v_src, r_trg.reshape(-1, 3)[idx].reshape(-1))
+        assert rel_err(v.reshape(-1, 3)[idx].reshape(-1), want) <= 1e-12
+
+
 def test_target_permutation_equivariance(sb):
     """Permuting the targets permutes the result bit-for-bit: a target's sum does not depend on its slot."""
     import torch

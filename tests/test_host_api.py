@@ -114,3 +114,27 @@ def test_cpp_host_layer_compiles_standalone(tmp_path):
                         "-L", os.path.join(ROOT, "sctl_b200"), "-lsctl_cuda", "-Wl,-rpath," + os.path.join(ROOT, "sctl_b200")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_sass_evidence_of_the_b200_design(sbm):
+    """cuobjdump of the shipped library: the shared-memory kernels stream sources with TMA bulk copies (UBLKCP) behind
+    mbarriers (SYNCS), seed the reciprocal square root with MUFU.RSQ64H, and the constant-bank kernels feed FP64
+    instructions with uniform-register operands loaded by LDCU (no vector LDC of the source records)."""
+    import shutil
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    txt = subprocess.run(["cuobjdump", "-sass", sbm.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = {m.group(1): m.group(2) for m in re.finditer(r"Function : (\S+)\n(.*?)(?=Function :|\Z)", txt, flags=re.S)}
+    smem = [b for n, b in funcs.items() if "eval_pairs_kernel" in n]
+    const = [b for n, b in funcs.items() if "eval_pairs_const_kernel" in n]
+    assert len(smem) >= 50 and len(const) >= 25
+    for body in smem:
+        assert "UBLKCP" in body and "SYNCS" in body
+    for n, body in funcs.items():
+        if "eval_pairs" in n and "IdLi" in n:
+            assert "MUFU.RSQ64H" in body, n
+    for body in const:
+        assert re.search(r"LDCU(\.\d+)? UR\d+, c\[0x3\]", body)
+        assert not re.search(r" LDC(\.\d+)? R\d+, c\[0x3\]", body)
+        assert len(re.findall(r"[DF](FMA|MUL|ADD) [^;]*UR\d+", body)) >= 40
+    assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", sbm.LIB_PATH], capture_output=True, text=True).stdout

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "eval_kernel.cuh"
+#include "eval_const_kernel.cuh"
 
 using namespace sctl_cuda;
 
@@ -177,6 +178,71 @@ void run_variant(Ctx& c, bool is_ref, int force_split = 0) {
   const double peak = sizeof(Real) == 8 ? c.peak64 : c.peak32;
   printf("%s kid=%d T=%d NW=%d R=%d RSQ=%d TILE=%4d ST=%d MINB=%d U=%d | regs=%3d occ=%d smem=%6zu grid=%5ux%-3u eff=%.3f | %8.3f ms %7.1f Gpair/s  F_alg-frac=%.3f  err=%.2e\n",
          sizeof(Real) == 8 ? "f64" : "f32", KID, T, NW, R, RSQ, TILE, STAGES, MINB, U, fa.numRegs, nb, Cfg::SMEM_BYTES, grid.x, grid.y, plan.wave_eff, best, rate * 1e-9,
+         rate * KerTraits<KID>::F_ALG * 1e-12 / peak, vmax > 0 ? dmax / vmax : 0.0);
+  fflush(stdout);
+}
+
+// constant-bank variant: time the whole host loop (copy chunk to the constant bank + launch) over all Ns sources
+template <class Real, int KID, int T, int NT, int RSQ, int U, int MINB>
+void run_const(Ctx& c, int n_sub = 1) {
+  constexpr int REC = RecTraits<Real, KID>::REC;
+  constexpr int K1 = KerTraits<KID>::K1;
+  constexpr int CH = const_chunk_records<Real, KID>();
+  auto kern = eval_pairs_const_kernel<Real, KID, T, NT, RSQ, U, MINB>;
+  int nb = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, 0));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, kern));
+  ConstEvalArgs<Real> a;
+  a.r_trg = (const Real*)c.r_trg;
+  a.v_trg = (Real*)c.v_trg;
+  a.Nt = c.Nt;
+  a.scale = scale_factor<Real>(KID);
+  const int tpb = NT * T;
+  dim3 grid((unsigned)((c.Nt + tpb - 1) / tpb), (unsigned)n_sub);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NT);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = n_sub;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = n_sub > 1 ? 1 : 0;
+  float best = 1e30f;
+  int launches = 0;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaMemsetAsync(a.v_trg, 0, sizeof(Real) * c.Nt * K1));
+    CK(cudaEventRecord(c.e0));
+    launches = 0;
+    for (int64_t s0 = 0; s0 < c.Ns; s0 += CH) {
+      const int n = (int)std::min<int64_t>(CH, c.Ns - s0);
+      CK(cudaMemcpyToSymbolAsync(c_src_pack, (const Real*)c.pack + s0 * REC, sizeof(Real) * n * REC, 0, cudaMemcpyDeviceToDevice));
+      a.n_rec = n;
+      a.sub_len = (n + n_sub - 1) / n_sub;
+      CK(cudaLaunchKernelEx(&cfg, kern, a));
+      launches++;
+    }
+    CK(cudaEventRecord(c.e1));
+    CK(cudaEventSynchronize(c.e1));
+    CK(cudaGetLastError());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, c.e0, c.e1));
+    if (rep > 0) best = std::min(best, ms);
+  }
+  std::vector<Real> h((size_t)c.Nt * K1), href((size_t)c.Nt * K1);
+  CK(cudaMemcpy(h.data(), a.v_trg, sizeof(Real) * c.Nt * K1, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(href.data(), c.v_ref, sizeof(Real) * c.Nt * K1, cudaMemcpyDeviceToHost));
+  double vmax = 0, dmax = 0;
+  for (size_t i = 0; i < h.size(); i++) {
+    vmax = std::max(vmax, std::fabs((double)href[i]));
+    dmax = std::max(dmax, std::fabs((double)h[i] - (double)href[i]));
+  }
+  const double rate = (double)c.Ns * c.Nt / (best * 1e-3);
+  const double peak = sizeof(Real) == 8 ? c.peak64 : c.peak32;
+  printf("%s CONST kid=%d T=%d NT=%d RSQ=%d U=%d MINB=%d CL=%d | regs=%3d occ=%d CH=%d launches=%d grid=%ux%u | %8.3f ms %7.1f Gpair/s  F_alg-frac=%.3f  err=%.2e\n",
+         sizeof(Real) == 8 ? "f64" : "f32", KID, T, NT, RSQ, U, MINB, n_sub, fa.numRegs, nb, CH, launches, grid.x, grid.y, best, rate * 1e-9,
          rate * KerTraits<KID>::F_ALG * 1e-12 / peak, vmax > 0 ? dmax / vmax : 0.0);
   fflush(stdout);
 }
