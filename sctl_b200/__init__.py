@@ -51,6 +51,7 @@ def load_library():
     L.sctl_cuda_last_timing.argtypes = [dp, dp, dp]
     L.sctl_cuda_last_plan.argtypes = [ip, ip, ip, ip, ip, ip, dp]
     L.sctl_cuda_fma_peak.argtypes = [i, C.c_double, dp]
+    L.sctl_cuda_set_option.argtypes = [C.c_char_p, i64]
     L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
     _lib = L
     return L
@@ -105,6 +106,11 @@ def last_plan():
     out = {k: x.value for k, x in zip(keys, v)}
     out["wave_eff"] = w.value
     return out
+
+
+def set_option(name, value):
+    """sctl_cuda_set_option: 'const_min_targets', 'wide_min_targets', 'few_max_targets' (Eval path selection)."""
+    _check(load_library().sctl_cuda_set_option(name.encode(), int(value)))
 
 
 def plan_eval(Ns, Nt, tpb, slots, min_chunk, max_split):

@@ -82,7 +82,19 @@ struct NcclApi {
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
+struct Options {
+  // Eval path selection by target count (sctl_cuda_set_option):
+  //   Nt >= const_min_targets : constant-bank chunk streaming (eval_const_kernel.cuh)
+  //   Nt <= few_max_targets   : shared-memory ring, all warps of a CTA share 32 targets and split the sources
+  //   Nt >= wide_min_targets  : shared-memory ring, 4 targets per thread, one CTA per SM
+  //   otherwise               : shared-memory ring, 2 targets per thread, two CTAs per SM
+  int64_t const_min_targets = 1 << 18;
+  int64_t few_max_targets = 2048;
+  int64_t wide_min_targets = 1 << 16;
+};
+
 struct Global {
+  Options opt;
   std::mutex mu;
   int n_gpus = 0;  // 0 = not initialised
   DeviceInfo dev[MAX_DEV];
@@ -163,11 +175,13 @@ template <class Real> int rsq_mode_for_digits(int digits) {
 template <class Real> struct Tune;
 template <> struct Tune<double> {
   static constexpr int T = 2, NW = 8, TILE = 256, STAGES = 3, MINB = 2;
+  static constexpr int WIDE_T = 4, WIDE_NW = 8, WIDE_TILE = 256, WIDE_STAGES = 3, WIDE_MINB = 1;
   static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 256, FEW_STAGES = 3, FEW_MINB = 2;
   static constexpr int CONST_T = 2, CONST_NT = 256, CONST_U = 4, CONST_MINB = 2;
 };
 template <> struct Tune<float> {
   static constexpr int T = 4, NW = 8, TILE = 512, STAGES = 3, MINB = 2;
+  static constexpr int WIDE_T = 4, WIDE_NW = 8, WIDE_TILE = 512, WIDE_STAGES = 3, WIDE_MINB = 2;
   static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 512, FEW_STAGES = 3, FEW_MINB = 2;
   static constexpr int CONST_T = 4, CONST_NT = 128, CONST_U = 2, CONST_MINB = 4;
 };
@@ -235,7 +249,6 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
 // Chunk-streaming path: for every CONST_PACK_BYTES of packed sources, copy them into the constant bank (device to
 // device, stream ordered) and launch eval_pairs_const_kernel over all targets.  Each launch costs a fixed ~20 us
 // (kernel boundary + cold constant cache), so the path is used only when a chunk x Nt is >= ~2 ms of work.
-constexpr int64_t CONST_MIN_TARGETS = 1 << 18;
 
 template <class Real, int KID, int RSQ>
 int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
@@ -289,9 +302,6 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   return 0;
 }
 
-// few-target threshold: below this many targets the MAIN grid cannot fill the GPU even with source splitting
-constexpr int64_t FEW_TARGETS = 2048;
-
 template <class Real, int KID, int RSQ>
 int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
   using Tn = Tune<Real>;
@@ -304,9 +314,11 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
     CU_TRY(cudaGetLastError());
   }
   int rc;
-  if (Nt >= CONST_MIN_TARGETS)
+  if (Nt >= g.opt.const_min_targets)
     rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, stream);
-  else if (Nt <= FEW_TARGETS)
+  else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8)
+    rc = launch_eval_cfg<Real, KID, Tn::WIDE_T, Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, 8 * Tn::WIDE_TILE, 64);
+  else if (Nt <= g.opt.few_max_targets)
     rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, Tn::FEW_TILE, 1024);
   else
     rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, 8 * Tn::TILE, 64);
@@ -796,6 +808,16 @@ int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes,
   if (ctas_per_sm) *ctas_per_sm = tl.ctas_per_sm;
   if (n_launches) *n_launches = tl.n_launches;
   if (wave_eff) *wave_eff = tl.wave_eff;
+  return 0;
+}
+
+int sctl_cuda_set_option(const char* name, int64_t value) {
+  if (!name) return fail("null option name");
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (!strcmp(name, "const_min_targets")) g.opt.const_min_targets = value;
+  else if (!strcmp(name, "few_max_targets")) g.opt.few_max_targets = value;
+  else if (!strcmp(name, "wide_min_targets")) g.opt.wide_min_targets = value;
+  else return fail("unknown option '%s'", name);
   return 0;
 }
 
