@@ -91,6 +91,7 @@ struct Options {
   int64_t const_min_targets = 1 << 18;
   int64_t few_max_targets = 2048;
   int64_t wide_min_targets = 1 << 16;
+  int64_t const_fp32 = 0;  // FP32 gains nothing from the constant-bank path (rates in profiles/): off by default
 };
 
 struct Global {
@@ -314,7 +315,7 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
     CU_TRY(cudaGetLastError());
   }
   int rc;
-  if (Nt >= g.opt.const_min_targets)
+  if (Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || g.opt.const_fp32))
     rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, stream);
   else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8)
     rc = launch_eval_cfg<Real, KID, Tn::WIDE_T, Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, 8 * Tn::WIDE_TILE, 64);
@@ -380,7 +381,11 @@ int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, in
 template <class Real, int KID>
 int kmat_device_k(int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, cudaStream_t stream) {
   constexpr int BT = 128;
-  dim3 grid((unsigned)((Nt + BT - 1) / BT), (unsigned)std::min<int64_t>(Ns, 32768));
+  // a CTA keeps its BT targets in registers and walks sources s = blockIdx.y, blockIdx.y + gridDim.y, ...; enough
+  // CTAs to fill the machine (~32 per SM), few enough that each one amortises its target loads over many rows
+  const int64_t n_tb = (Nt + BT - 1) / BT;
+  const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(Ns, (148 * 32 + n_tb - 1) / n_tb));
+  dim3 grid((unsigned)n_tb, (unsigned)std::min<int64_t>(rows, 65535));
   const Real scale = scale_factor<Real>(KID);
   switch (rsq_mode_for_digits<Real>(digits)) {
     case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale); break;
@@ -817,6 +822,7 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "const_min_targets")) g.opt.const_min_targets = value;
   else if (!strcmp(name, "few_max_targets")) g.opt.few_max_targets = value;
   else if (!strcmp(name, "wide_min_targets")) g.opt.wide_min_targets = value;
+  else if (!strcmp(name, "const_fp32")) g.opt.const_fp32 = value;
   else return fail("unknown option '%s'", name);
   return 0;
 }

@@ -79,6 +79,7 @@ def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
     k0, k1, nd = cases.KERNELS[kernel]
     Nt, Ns = (1 << 18) + 77, 4500
     tdt = torch.float64 if dtype == np.float64 else torch.float32
+    sb.set_option("const_fp32", 1)  # the FP32 instantiations exist and must be right even though FP64 alone uses them by default
     r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
     pre = (synth.splitmix_u01(13, Nt * k1) - 0.5).astype(dtype)
     d = [None if a is None else torch.from_numpy(a).cuda() for a in (r_src, n_src, v_src, r_trg)]
@@ -97,6 +98,7 @@ def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
     sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_w)
     torch.cuda.synchronize()
     assert torch.equal(d_v, d_w)
+    sb.set_option("const_fp32", 0)
 
 
 def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):

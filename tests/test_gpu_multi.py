@@ -1,0 +1,54 @@
+"""Multi-GPU tests (need >= 2 visible GPUs; skipped otherwise): the C library's own single-process sharding
+(sctl_cuda_init(n): target shards + NCCL source replication, csrc/sctl_cuda.cu) and the torchrun layer
+(sctl_b200.sharded over NCCL) must reproduce the single-GPU result bit for bit -- no reduction is involved, so the
+per-target summation order does not depend on the number of GPUs."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _need_gpus(sb, n):
+    if sb.device_count() < n:
+        pytest.skip("needs %d GPUs, %d visible" % (n, sb.device_count()))
+
+
+@pytest.mark.parametrize("kernel", ["Stokes3D_FxU", "Laplace3D_DxU"])
+def test_library_sharding_matches_single_gpu(sb, cpu_oracle, kernel):
+    _need_gpus(sb, 2)
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    K = sb.KERNELS[kernel]
+    Ns, Nt = 60001, 40003  # > 1e9 pairs: the host entry shards; ragged so the block partition is uneven
+    r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd)
+    pre = synth.splitmix_u01(17, Nt * k1) - 0.5
+    try:
+        assert sb.init(1) == 1
+        one = K.Eval(pre.copy(), r_trg, r_src, n_src, v_src)
+        n = sb.init(0)  # all visible GPUs
+        assert n == sb.device_count() >= 2
+        many = K.Eval(pre.copy(), r_trg, r_src, n_src, v_src)
+        t = sb.last_timing()
+        assert t["kernel_ms"] > 0
+    finally:
+        sb.init(1)
+    idx = np.arange(64) * (Nt // 64)
+    want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg.reshape(-1, 3)[idx].reshape(-1), v_trg=pre.reshape(-1, k1)[idx].reshape(-1))
+    assert rel_err(many.reshape(-1, k1)[idx].reshape(-1), want) <= 1e-12
+    assert rel_err(many, one) <= 1e-13  # shards may pick a different source split than the full problem
+
+
+def test_torchrun_sharded_eval_two_ranks(sb):
+    _need_gpus(sb, 2)
+    script = os.path.join(ROOT, "tests", "_torchrun_sharded.py")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29631", script],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -221,6 +221,30 @@ def test_eval_equals_kernel_matrix_apply_and_linearity(sb, kernel):
     assert rel_err(vb, 2.0 * v - 3.0 * va) <= 1e-12
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_every_eval_path_agrees(sb, cpu_oracle, kernel, dtype):
+    """The four launch paths (few-target, 2-per-thread, 4-per-thread, constant-bank) forced on the same inputs."""
+    from sctl_b200 import synth
+    K = sb.KERNELS[kernel]
+    k0, k1, nd = cases.KERNELS[kernel]
+    Ns, Nt = 2900, 1500
+    r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
+    want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg, dtype=dtype)
+    big = 1 << 40
+    paths = {"few": dict(few_max_targets=big, wide_min_targets=big, const_min_targets=big), "main": dict(few_max_targets=0, wide_min_targets=big, const_min_targets=big),
+             "wide": dict(few_max_targets=0, wide_min_targets=1, const_min_targets=big), "const": dict(few_max_targets=0, wide_min_targets=big, const_min_targets=1, const_fp32=1)}
+    try:
+        for name, opts in paths.items():
+            for k, v in opts.items():
+                sb.set_option(k, v)
+            got = K.Eval(None, r_trg, r_src, n_src, v_src, dtype=dtype)
+            assert rel_err(got, want) <= TOL[dtype], (name, kernel, rel_err(got, want), sb.last_plan())
+    finally:
+        for k, v in dict(few_max_targets=2048, wide_min_targets=1 << 16, const_min_targets=1 << 18, const_fp32=0).items():
+            sb.set_option(k, v)
+
+
 def test_deterministic_and_split_invariant(sb):
     """Same inputs -> bit-identical outputs (no atomics), also when the planner splits the source range."""
     from sctl_b200 import synth
