@@ -30,15 +30,16 @@ enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
 //   RSQ_CUBIC : y = y0 * (1 + e*(1/2 + 3/8 e))        5 FP64 instr, error ~ 5/16 e^3 (~1 ulp)
 // SCTL's AVX-512 recipe (14-bit seed, 2 Newton steps, deferred scaling) costs 7.
 // Mask: like _mm512_maskz_rsqrt14_pd in the reference (intrin-wrapper.hpp:3403) the SEED is zeroed and the
-// refinement then keeps it zero (e = 1, y0*e = 0).  The test is one integer range check on the high word
-// (ALU pipe, no branch): zero, NaN, Inf and subnormal r2 are masked.  Subnormal r2 (|dx| < 1.5e-154) is
-// treated as coincident; the reference overflows to Inf/NaN there for every kernel but Laplace FxU.
+// refinement then keeps it zero (e = 1, y0 * (1 + ...) = 0).  Subnormal r2 (|dx| < 1.5e-154) is treated as
+// coincident; the reference overflows to Inf/NaN there for every kernel but Laplace FxU.
 template <int MODE> __device__ __forceinline__ double rsqrt_masked(double x) {
-  const int hi = __double2hiint(x);
-  double y0;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
-  const bool ok = (unsigned)(hi - 0x00100000) < 0x7fe00000u;  // positive, normal, finite
-  y0 = __hiloint2double(ok ? __double2hiint(y0) : 0, 0);
+  // One signed compare on the high word: false for zero, subnormal and negative inputs (NaN/Inf propagate as NaN,
+  // exactly as in the reference), then a select on the seed's high word; its low word is zero anyway.  Every
+  // register-reading instruction competes with the DFMA stream for register-file bandwidth on B200
+  // (tools/probe.cu, probe4), so the mask is kept to compare + select.
+  double ys;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ys) : "d"(x));
+  const double y0 = __hiloint2double(__double2hiint(x) >= 0x00100000 ? __double2hiint(ys) : 0, 0);
   if (MODE == RSQ_SEED) return y0;
   const double e = fma(-x, y0 * y0, 1.0);
   // Written as y0 * (1 + e*p) rather than y0 + (y0*e)*p: every instruction then reads at most two distinct
@@ -51,13 +52,12 @@ template <int MODE> __device__ __forceinline__ double rsqrt_masked(double x) {
 // reference computes for float by default (digits = (int)(23*0.30103) = 6, vec.txx:376).  digits >= 7 adds one
 // Newton step on the FP32 pipe.  Same masking rule as FP64 (subnormal r2 means |dx| < 1.1e-19).
 template <int MODE> __device__ __forceinline__ float rsqrt_masked(float x) {
-  float y0;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
-  const bool ok = __float_as_uint(x) - 0x00800000u < 0x7f000000u;  // positive, normal, finite
-  y0 = ok ? y0 : 0.0f;
+  float ys;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ys) : "f"(x));
+  const float y0 = __float_as_int(x) >= 0x00800000 ? ys : 0.0f;
   if (MODE == RSQ_SEED) return y0;
   const float e = fmaf(-x, y0 * y0, 1.0f);
-  return fmaf(y0 * e, 0.5f, y0);
+  return y0 * fmaf(e, 0.5f, 1.0f);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -67,6 +67,109 @@ template <int MODE> void run(const char* what, int sms, const double* in, double
          n / (best * 1e-3) / sms / 1.965e9, 2 * n / (best * 1e-3) * 1e-12);
 }
 
+// What does each auxiliary instruction of the pair loop cost the FP64 pipe?  24 two-operand DFMA per iteration plus
+// EXTRA: 0 nothing | 1 one MUFU.RSQ64H | 2 one MUFU.RSQ (f32) | 3 four ALU ops (add/compare/select/mov) | 4 two LDCU.64 | 5 all
+__constant__ double cprobe[1024];
+template <int EXTRA> __global__ void __launch_bounds__(256) probe4(int iters, const double* __restrict__ in, double* out) {
+  double a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { a[i] = in[i] + threadIdx.x; b[i] = in[8 + i] * 1e-3 + threadIdx.x * 1e-9; }
+  double x = 2.0 + threadIdx.x;
+  float xf = 2.0f + threadIdx.x;
+  int k = threadIdx.x;
+  double cs = 0;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 3; u++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = fma(b[i], b[i], a[i]);
+    if (EXTRA == 1 || EXTRA == 5) {
+      double y;
+      asm volatile("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+      x = __hiloint2double(__double2hiint(x) ^ (__double2hiint(y) & 1), __double2loint(x));
+    }
+    if (EXTRA == 2) {
+      float y;
+      asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(xf));
+      xf = __uint_as_float(__float_as_uint(xf) ^ (__float_as_uint(y) & 1));
+    }
+    if (EXTRA == 3 || EXTRA == 5) {
+      int t = k + 0x00100000;
+      k = ((unsigned)t < 0x7fe00000u) ? (t ^ it) : 0;
+    }
+    if (EXTRA == 4 || EXTRA == 5) cs += cprobe[(it * 2) & 1023] + cprobe[(it * 2 + 1) & 1023];
+  }
+  double s = x + xf + k + cs;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += a[i];
+  if (s == -1.0) out[0] = s;
+}
+template <int EXTRA> void run4(const char* what, int sms, const double* in, double* out) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int iters = 40000, blocks = sms * 2, threads = 256;
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    probe4<EXTRA><<<blocks, threads>>>(iters, in, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double n = (double)iters * 24 * blocks * threads;
+  printf("probe4 24 DFMA + %-40s %8.3f ms  %6.2f DFMA-lanes/clk/SM (@1.965GHz)\n", what, best, n / (best * 1e-3) / sms / 1.965e9);
+}
+
+// Triples that share one multiplicand (the accumulate pattern acc_i = fma(rinv, w_i, acc_i)):
+// MODE 0: rinv in slot A; MODE 1: rinv in slot B; MODE 2: slot A plus a 2-operand DMUL between groups
+template <int MODE> __global__ void __launch_bounds__(256) probe3(int iters, const double* __restrict__ in, double* out) {
+  constexpr int G = 4;
+  double a[3 * G], w[3 * G], r[G];
+#pragma unroll
+  for (int i = 0; i < 3 * G; i++) { a[i] = in[i] + threadIdx.x; w[i] = in[12 + i] * 1e-3 + threadIdx.x * 1e-9; }
+#pragma unroll
+  for (int g = 0; g < G; g++) r[g] = in[30 + g] * 0.999 + threadIdx.x * 1e-10;
+  const double m = in[40] + threadIdx.x * 1e-11;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          if (MODE == 1) a[3 * g + i] = fma(w[3 * g + i], r[g], a[3 * g + i]);
+          else a[3 * g + i] = fma(r[g], w[3 * g + i], a[3 * g + i]);
+        }
+        if (MODE == 2) r[g] = r[g] * m;
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 3 * G; i++) s += a[i] + w[i];
+#pragma unroll
+  for (int g = 0; g < G; g++) s += r[g];
+  if (s == -1.0) out[0] = s;
+}
+
+template <int MODE> void run3(const char* what, int sms, const double* in, double* out, int threads, int blocks_per_sm) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int iters = 20000, blocks = sms * blocks_per_sm;
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    probe3<MODE><<<blocks, threads>>>(iters, in, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double n = (double)iters * 4 * (MODE == 2 ? 16 : 12) * blocks * threads;
+  printf("probe3 %-43s thr=%3d blk/SM=%d  %8.3f ms  %6.2f FP64-instr-lanes/clk/SM (@1.965GHz)\n", what, threads, blocks_per_sm, best, n / (best * 1e-3) / sms / 1.965e9);
+}
+
 int main() {
   cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
   const int sms = prop.multiProcessorCount;
@@ -85,6 +188,18 @@ int main() {
     run<7>("3 distinct + 2 int ops per DFMA", sms, in, out, threads, bps);
     run<8>("3 distinct + LDS.128 per 4 DFMA", sms, in, out, threads, bps);
     run<9>("fma(b,c,a) rotating dest", sms, in, out, threads, bps);
+  }
+  run4<0>("nothing", sms, in, out);
+  run4<1>("1 MUFU.RSQ64H", sms, in, out);
+  run4<2>("1 MUFU.RSQ (f32)", sms, in, out);
+  run4<3>("4 ALU ops", sms, in, out);
+  run4<4>("2 LDCU.64 (+1 DADD)", sms, in, out);
+  run4<5>("MUFU.RSQ64H + 4 ALU + 2 LDCU", sms, in, out);
+  for (int cfg = 0; cfg < 4; cfg++) {
+    const int threads = 128, bps = cfg == 0 ? 1 : cfg == 1 ? 2 : cfg == 2 ? 4 : 8;  // 1, 2, 4, 8 warps per sub-partition
+    run3<0>("triples, shared operand in slot A", sms, in, out, threads, bps);
+    run3<1>("triples, shared operand in slot B", sms, in, out, threads, bps);
+    run3<2>("triples (slot A) + DMUL between groups", sms, in, out, threads, bps);
   }
   return 0;
 }
