@@ -37,13 +37,15 @@ template <class Real> struct ConstEvalArgs {
 
 template <class Real, int KID> constexpr int const_chunk_records() { return CONST_PACK_BYTES / (RecTraits<Real, KID>::REC * (int)sizeof(Real)); }
 
+// NT is the LARGEST block the kernel may be launched with; the host picks blockDim.x = 32 * (warps per CTA) <= NT so
+// that every SM gets the same number of warps (see launch_eval_const in sctl_cuda.cu).
 template <class Real, int KID, int T, int NT, int RSQ, int U, int MINB>
 __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstEvalArgs<Real> a) {
   constexpr int REC = RecTraits<Real, KID>::REC;
   constexpr int K1 = KerTraits<KID>::K1;
   __shared__ Real red[T * K1 * NT];  // cluster reduction buffer
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t t_base = ((int64_t)blockIdx.x * (NT / 32) + warp) * (32 * T) + lane;
+  const int64_t t_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * (32 * T) + lane;
   Real xt[T][3], acc[T][K1];
 #pragma unroll
   for (int j = 0; j < T; j++) {

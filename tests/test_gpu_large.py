@@ -72,13 +72,14 @@ def test_config4_kernels_fp32_fp64_large(sb, cpu_oracle, kernel):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("kernel", list(cases.KERNELS))
 def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
-    """Nt >= 2^18 takes the chunk-streaming path (sources through the constant bank into uniform registers, one launch
+    """Large Nt (>= 2^19 by default; forced at 2^18 here) takes the chunk-streaming path (sources through the constant bank into uniform registers, one launch
     per chunk, 2-CTA clusters at this size): several chunks, ragged last chunk, pre-filled v_trg, every kernel."""
     import torch
     from sctl_b200 import synth
     k0, k1, nd = cases.KERNELS[kernel]
     Nt, Ns = (1 << 18) + 77, 4500
     tdt = torch.float64 if dtype == np.float64 else torch.float32
+    sb.set_option("const_min_targets", 1 << 18)
     sb.set_option("const_fp32", 1)  # the FP32 instantiations exist and must be right even though FP64 alone uses them by default
     r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
     pre = (synth.splitmix_u01(13, Nt * k1) - 0.5).astype(dtype)
@@ -99,6 +100,7 @@ def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
     torch.cuda.synchronize()
     assert torch.equal(d_v, d_w)
     sb.set_option("const_fp32", 0)
+    sb.set_option("const_min_targets", 1 << 19)
 
 
 def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
@@ -109,6 +111,7 @@ def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
     from sctl_b200 import synth
     Nt, Ns = 1 << 18, 3000
     res = {}
+    sb.set_option("const_min_targets", 1 << 18)
 
     def work(i):
         torch.cuda.set_device(0)
@@ -131,6 +134,7 @@ def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
         idx = np.arange(100) * (Nt // 100)
         want = cpu_oracle.eval("Stokes3D_FxU", r_src, None, v_src, r_trg.reshape(-1, 3)[idx].reshape(-1))
         assert rel_err(v.reshape(-1, 3)[idx].reshape(-1), want) <= 1e-12
+    sb.set_option("const_min_targets", 1 << 19)
 
 
 def test_target_permutation_equivariance(sb):

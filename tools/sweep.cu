@@ -184,7 +184,8 @@ void run_variant(Ctx& c, bool is_ref, int force_split = 0) {
 
 // constant-bank variant: time the whole host loop (copy chunk to the constant bank + launch) over all Ns sources
 template <class Real, int KID, int T, int NT, int RSQ, int U, int MINB>
-void run_const(Ctx& c, int n_sub = 1) {
+void run_const(Ctx& c, int n_sub = 1, int wpc = 0) {
+  if (wpc == 0) wpc = NT / 32;
   constexpr int REC = RecTraits<Real, KID>::REC;
   constexpr int K1 = KerTraits<KID>::K1;
   constexpr int CH = const_chunk_records<Real, KID>();
@@ -198,11 +199,11 @@ void run_const(Ctx& c, int n_sub = 1) {
   a.v_trg = (Real*)c.v_trg;
   a.Nt = c.Nt;
   a.scale = scale_factor<Real>(KID);
-  const int tpb = NT * T;
+  const int tpb = 32 * wpc * T;
   dim3 grid((unsigned)((c.Nt + tpb - 1) / tpb), (unsigned)n_sub);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(NT);
+  cfg.blockDim = dim3(32 * wpc);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
@@ -241,9 +242,47 @@ void run_const(Ctx& c, int n_sub = 1) {
   }
   const double rate = (double)c.Ns * c.Nt / (best * 1e-3);
   const double peak = sizeof(Real) == 8 ? c.peak64 : c.peak32;
-  printf("%s CONST kid=%d T=%d NT=%d RSQ=%d U=%d MINB=%d CL=%d | regs=%3d occ=%d CH=%d launches=%d grid=%ux%u | %8.3f ms %7.1f Gpair/s  F_alg-frac=%.3f  err=%.2e\n",
-         sizeof(Real) == 8 ? "f64" : "f32", KID, T, NT, RSQ, U, MINB, n_sub, fa.numRegs, nb, CH, launches, grid.x, grid.y, best, rate * 1e-9,
+  printf("%s CONST kid=%d T=%d NT=%d wpc=%d RSQ=%d U=%d MINB=%d CL=%d | regs=%3d occ=%d CH=%d launches=%d grid=%ux%u | %8.3f ms %7.1f Gpair/s  F_alg-frac=%.3f  err=%.2e\n",
+         sizeof(Real) == 8 ? "f64" : "f32", KID, T, NT, wpc, RSQ, U, MINB, n_sub, fa.numRegs, nb, CH, launches, grid.x, grid.y, best, rate * 1e-9,
          rate * KerTraits<KID>::F_ALG * 1e-12 / peak, vmax > 0 ? dmax / vmax : 0.0);
+  fflush(stdout);
+}
+
+// Where does the per-launch cost of the constant-bank path go?  Same launches, three ways.
+template <class Real, int KID, int T, int NT, int RSQ, int U, int MINB>
+void run_const_breakdown(Ctx& c) {
+  constexpr int REC = RecTraits<Real, KID>::REC;
+  constexpr int CH = const_chunk_records<Real, KID>();
+  auto kern = eval_pairs_const_kernel<Real, KID, T, NT, RSQ, U, MINB>;
+  ConstEvalArgs<Real> a;
+  a.r_trg = (const Real*)c.r_trg;
+  a.v_trg = (Real*)c.v_trg;
+  a.Nt = c.Nt;
+  a.scale = scale_factor<Real>(KID);
+  a.n_rec = CH;
+  a.sub_len = CH;
+  const int tpb = NT * T;
+  dim3 grid((unsigned)((c.Nt + tpb - 1) / tpb), 1);
+  const int n_launch = (int)((c.Ns + CH - 1) / CH);
+  for (int mode = 0; mode < 4; mode++) {
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+      CK(cudaEventRecord(c.e0));
+      for (int i = 0; i < n_launch; i++) {
+        if (mode == 1 || mode == 2) CK(cudaMemcpyToSymbolAsync(c_src_pack, (const Real*)c.pack + (int64_t)(i % 64) * CH * REC, sizeof(Real) * CH * REC, 0, cudaMemcpyDeviceToDevice));
+        if (mode == 3) CK(cudaMemcpyAsync(c.partial, (const Real*)c.pack + (int64_t)(i % 64) * CH * REC, sizeof(Real) * CH * REC, cudaMemcpyDeviceToDevice));
+        if (mode != 1) kern<<<grid, NT>>>(a);
+      }
+      CK(cudaEventRecord(c.e1));
+      CK(cudaEventSynchronize(c.e1));
+      CK(cudaGetLastError());
+      float ms;
+      CK(cudaEventElapsedTime(&ms, c.e0, c.e1));
+      best = std::min(best, ms);
+    }
+    const char* what[4] = {"kernel only (constant bank untouched)", "memcpyToSymbol only", "memcpyToSymbol + kernel", "plain D2D memcpy (not to the bank) + kernel"};
+    printf("breakdown Nt=%lld grid=%u x %d launches: %-46s %9.3f ms total, %8.2f us per launch\n", (long long)c.Nt, grid.x, n_launch, what[mode], best, best * 1e3 / n_launch);
+  }
   fflush(stdout);
 }
 
