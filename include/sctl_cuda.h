@@ -111,6 +111,9 @@ int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes,
  *                       (FP64 only unless "const_fp32" is set to 1);
  *   "wide_min_targets"  (default 2^16): at or above (FP64), 4 targets per thread, one CTA per SM;
  *   "few_max_targets"   (default 2048): at or below, the warps of a CTA share 32 targets and split the sources.
+ *   "probe_min_pairs"   (default 2e9): at or above Ns*Nt, Eval first checks (O(Ns+Nt), on the device) whether any source
+ *                       and target (nearly) coincide and lets the pair kernels drop the r^2 == 0 mask when none do;
+ *                       <= 0 disables the check.  Results are bit-identical either way.
  * Results agree to rounding whichever path runs; the knobs exist for tuning and for tests. */
 int sctl_cuda_set_option(const char* name, int64_t value);
 

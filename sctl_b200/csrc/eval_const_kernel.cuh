@@ -25,6 +25,10 @@ namespace sctl_cuda {
 
 constexpr int CONST_PACK_BYTES = 64 * 1024 - 1024;  // leave room for the compiler's own bank-3 constants
 __constant__ double c_src_pack[CONST_PACK_BYTES / 8];
+// [0]: the coincidence probe's verdict for the call in flight (0 = no source/target pair can have r2 < 2^-1022, so the
+// unmasked loop is exact).  Copied device-to-device from the probe's flag, so the choice needs no host round trip, and
+// read with LDCU, so the branch on it is uniform and the loops keep their uniform-register operands.
+__constant__ int c_eval_must_mask[4];
 
 template <class Real> struct ConstEvalArgs {
   const Real* r_trg;  // [Nt][3]
@@ -32,6 +36,7 @@ template <class Real> struct ConstEvalArgs {
   int64_t Nt;
   int n_rec;          // records in the constant bank for this launch
   int sub_len;        // records per cluster rank (grid.y slice)
+  int allow_unmasked; // this call ran the coincidence probe: c_eval_must_mask is meaningful
   Real scale;
 };
 
@@ -58,11 +63,20 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
   // Loop bounds are kept in a form ptxas recognises as warp-uniform, otherwise it falls back to vector LDC.
   const Real* src = reinterpret_cast<const Real*>(c_src_pack) + (int)blockIdx.y * a.sub_len * REC;
   const int n = (blockIdx.y + 1 == gridDim.y) ? a.n_rec - (int)blockIdx.y * a.sub_len : a.sub_len;
+  if (a.allow_unmasked && c_eval_must_mask[0] == 0) {
 #pragma unroll U
-  for (int s = 0; s < n; s++) {
-    const Real* rec = src + s * REC;  // uniform address: LDCU into uniform registers
+    for (int s = 0; s < n; s++) {
+      const Real* rec = src + s * REC;  // uniform address: LDCU into uniform registers
 #pragma unroll
-    for (int j = 0; j < T; j++) pair_update<KID, RSQ>(acc[j], xt[j], rec);
+      for (int j = 0; j < T; j++) pair_update<KID, RSQ, false>(acc[j], xt[j], rec);
+    }
+  } else {
+#pragma unroll U
+    for (int s = 0; s < n; s++) {
+      const Real* rec = src + s * REC;
+#pragma unroll
+      for (int j = 0; j < T; j++) pair_update<KID, RSQ, true>(acc[j], xt[j], rec);
+    }
   }
   if (gridDim.y > 1) {
     // grid.y == cluster size: rank 0 adds the other ranks' partial sums in rank order

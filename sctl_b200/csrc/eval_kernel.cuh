@@ -109,6 +109,7 @@ template <class Real> struct EvalArgs {
   int64_t chunk;      // sources per grid.y slice
   int n_split;
   Real scale;
+  const int* must_mask;  // device flag from coincidence_probe_kernel (nullptr: always mask r2 == 0 pairs)
 };
 
 template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES> struct EvalConfig {
@@ -125,13 +126,32 @@ template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAG
   static_assert(R == 1 || (size_t)NW * T * K1 * 32 * sizeof(Real) <= STAGES * STAGE_BYTES, "reduction scratch must fit in the ring");
 };
 
+// One tile of packed records against this thread's T register-resident targets.
+template <class Real, int KID, int T, int R, int RSQ, int U, bool MASK>
+__device__ __forceinline__ void consume_tile(const Real* tile, int n, int rep, Real (&acc)[T][KerTraits<KID>::K1], const Real (&xt)[T][3]) {
+  constexpr int REC = RecTraits<Real, KID>::REC;
+  constexpr int W = 16 / (int)sizeof(Real);
+  using Vec16 = typename std::conditional<sizeof(Real) == 8, double2, float4>::type;
+#pragma unroll U
+  for (int s = rep; s < n; s += R) {
+    Real rec[REC];
+    const Vec16* p = reinterpret_cast<const Vec16*>(tile + s * REC);
+#pragma unroll
+    for (int q = 0; q < REC / W; q++) {
+      const Vec16 v = p[q];
+#pragma unroll
+      for (int c = 0; c < W; c++) rec[q * W + c] = ((const Real*)&v)[c];
+    }
+#pragma unroll
+    for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec);
+  }
+}
+
 template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES, int MINB, int U = 2>
 __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const EvalArgs<Real> a) {
   using Cfg = EvalConfig<Real, KID, T, NW, R, RSQ, TILE, STAGES>;
   constexpr int REC = Cfg::REC;
   constexpr int K1 = Cfg::K1;
-  constexpr int W = 16 / (int)sizeof(Real);
-  using Vec16 = typename std::conditional<sizeof(Real) == 8, double2, float4>::type;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Real* ring = reinterpret_cast<Real*>(smem_raw);
@@ -187,30 +207,15 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const E
     for (int k = 0; k < K1; k++) acc[j][k] = 0;
   }
 
+  const bool unmasked = a.must_mask != nullptr && a.must_mask[0] == 0;  // same value in every thread of the grid
   for (int i = 0; i < n_tiles; i++) {
     const int st = i % STAGES;
     mbar_wait(&full[st], (i / STAGES) & 1);
     const Real* tile = ring + st * Cfg::STAGE_REALS;
     const int64_t rem = n_src - (int64_t)i * TILE;
     const int n = (int)(rem < TILE ? rem : TILE);
-#pragma unroll U
-    for (int s = rep; s < n; s += R) {
-      Real rec[REC];
-      const Vec16* p = reinterpret_cast<const Vec16*>(tile + s * REC);
-#pragma unroll
-      for (int q = 0; q < REC / W; q++) {
-        const Vec16 v = p[q];
-        if (sizeof(Real) == 8) {
-          rec[q * W + 0] = ((const Real*)&v)[0];
-          rec[q * W + 1] = ((const Real*)&v)[1];
-        } else {
-#pragma unroll
-          for (int c = 0; c < W; c++) rec[q * W + c] = ((const Real*)&v)[c];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < T; j++) pair_update<KID, RSQ>(acc[j], xt[j], rec);
-    }
+    if (unmasked) consume_tile<Real, KID, T, R, RSQ, U, false>(tile, n, rep, acc, xt);
+    else consume_tile<Real, KID, T, R, RSQ, U, true>(tile, n, rep, acc, xt);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
   }

@@ -32,14 +32,17 @@ enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
 // Mask: like _mm512_maskz_rsqrt14_pd in the reference (intrin-wrapper.hpp:3403) the SEED is zeroed and the
 // refinement then keeps it zero (e = 1, y0 * (1 + ...) = 0).  Subnormal r2 (|dx| < 1.5e-154) is treated as
 // coincident; the reference overflows to Inf/NaN there for every kernel but Laplace FxU.
-template <int MODE> __device__ __forceinline__ double rsqrt_masked(double x) {
+// MASK = false drops the compare + select.  It is bit-identical to MASK = true whenever r2 >= 2^-1022 (or NaN/Inf),
+// and the host only selects it after coincidence_probe_kernel has shown that no (source, target) pair can have a
+// smaller r2 (eval_kernel.cuh); the two instructions cost ~3 % of the Stokes pair (profiles/r1_whatif.txt).
+template <int MODE, bool MASK = true> __device__ __forceinline__ double rsqrt_masked(double x) {
   // One signed compare on the high word: false for zero, subnormal and negative inputs (NaN/Inf propagate as NaN,
   // exactly as in the reference), then a select on the seed's high word; its low word is zero anyway.  Every
   // register-reading instruction competes with the DFMA stream for register-file bandwidth on B200
   // (tools/probe.cu, probe4), so the mask is kept to compare + select.
   double ys;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ys) : "d"(x));
-  const double y0 = __hiloint2double(__double2hiint(x) >= 0x00100000 ? __double2hiint(ys) : 0, 0);
+  const double y0 = MASK ? __hiloint2double(__double2hiint(x) >= 0x00100000 ? __double2hiint(ys) : 0, 0) : ys;
   if (MODE == RSQ_SEED) return y0;
   const double e = fma(-x, y0 * y0, 1.0);
   // Written as y0 * (1 + e*p) rather than y0 + (y0*e)*p: every instruction then reads at most two distinct
@@ -51,10 +54,10 @@ template <int MODE> __device__ __forceinline__ double rsqrt_masked(double x) {
 // FP32.  Seed = MUFU.RSQ (2^-22 relative error): that already meets approx_rsqrt<digits<=6>, which is what the
 // reference computes for float by default (digits = (int)(23*0.30103) = 6, vec.txx:376).  digits >= 7 adds one
 // Newton step on the FP32 pipe.  Same masking rule as FP64 (subnormal r2 means |dx| < 1.1e-19).
-template <int MODE> __device__ __forceinline__ float rsqrt_masked(float x) {
+template <int MODE, bool MASK = true> __device__ __forceinline__ float rsqrt_masked(float x) {
   float ys;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ys) : "f"(x));
-  const float y0 = __float_as_int(x) >= 0x00800000 ? ys : 0.0f;
+  const float y0 = MASK ? (__float_as_int(x) >= 0x00800000 ? ys : 0.0f) : ys;
   if (MODE == RSQ_SEED) return y0;
   const float e = fmaf(-x, y0 * y0, 1.0f);
   return y0 * fmaf(e, 0.5f, 1.0f);
@@ -158,14 +161,14 @@ template <class Real> struct PairApply<STOKES3D_DXU, Real> {
 };
 
 // One source-target pair, starting from coordinates.
-template <int KID, int RSQ, class Real>
+template <int KID, int RSQ, bool MASK = true, class Real>
 __device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], const Real (&xt)[3], const Real* s) {
   Real dx[3];
   dx[0] = xt[0] - s[0];
   dx[1] = xt[1] - s[1];
   dx[2] = xt[2] - s[2];
   const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
-  const Real rinv = rsqrt_masked<RSQ>(r2);
+  const Real rinv = rsqrt_masked<RSQ, MASK>(r2);
   PairApply<KID, Real>::run(acc, dx, rinv, s);
 }
 

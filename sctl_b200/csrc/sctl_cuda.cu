@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/sctl_cuda.h"
+#include "coincidence.cuh"
 #include "eval_const_kernel.cuh"
 #include "eval_kernel.cuh"
 #include "kmat_kernel.cuh"
@@ -92,6 +93,9 @@ struct Options {
   int64_t few_max_targets = 2048;
   int64_t wide_min_targets = 1 << 16;
   int64_t const_fp32 = 0;  // FP32 gains nothing from the constant-bank path (rates in profiles/): off by default
+  // Above this many pairs Eval first runs the O(Ns+Nt) coincidence probe (coincidence.cuh) and lets the pair kernels
+  // drop the r2 == 0 mask when no source/target pair can need it.  <= 0 disables the probe (always mask).
+  int64_t probe_min_pairs = 2000000000LL;
 };
 
 struct Global {
@@ -193,7 +197,7 @@ struct OccCache {
 };
 
 template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES, int MINB>
-int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, cudaStream_t stream, int min_chunk, int max_split) {
+int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, const int* must_mask, cudaStream_t stream, int min_chunk, int max_split) {
   using Cfg = EvalConfig<Real, KID, T, NW, R, RSQ, TILE, STAGES>;
   auto kern = eval_pairs_kernel<Real, KID, T, NW, R, RSQ, TILE, STAGES, MINB>;
   static OccCache occ;
@@ -223,6 +227,7 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
   a.chunk = plan.chunk;
   a.n_split = plan.n_split;
   a.scale = scale_factor<Real>(KID);
+  a.must_mask = must_mask;
   constexpr int K1 = KerTraits<KID>::K1;
   int n_launches = 1;
   if (plan.n_split > 1) CU_TRY(cudaMallocAsync((void**)&a.partial, sizeof(Real) * (size_t)plan.n_split * Nt * K1, stream));
@@ -252,7 +257,7 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
 // (kernel boundary + cold constant cache), so the path is used only when a chunk x Nt is >= ~2 ms of work.
 
 template <class Real, int KID, int RSQ>
-int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
+int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, const int* must_mask, cudaStream_t stream) {
   using Tn = Tune<Real>;
   constexpr int T = Tn::CONST_T, NT = Tn::CONST_NT;
   constexpr int REC = RecTraits<Real, KID>::REC;
@@ -266,6 +271,7 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   a.r_trg = r_trg;
   a.v_trg = v_trg;
   a.Nt = Nt;
+  a.allow_unmasked = must_mask != nullptr;
   a.scale = scale_factor<Real>(KID);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_tb, (unsigned)cl);
@@ -283,6 +289,7 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   std::lock_guard<std::mutex> lk(di.const_mu);
   if (!di.const_done) CU_TRY(cudaEventCreateWithFlags(&di.const_done, cudaEventDisableTiming));
   else CU_TRY(cudaStreamWaitEvent(stream, di.const_done, 0));  // the previous user of the constant bank, on any stream
+  if (must_mask) CU_TRY(cudaMemcpyToSymbolAsync(c_eval_must_mask, must_mask, sizeof(int), 0, cudaMemcpyDeviceToDevice, stream));
   int launches = 0;
   for (int64_t s0 = 0; s0 < Ns; s0 += CH) {
     const int n = (int)std::min<int64_t>(CH, Ns - s0);
@@ -314,15 +321,32 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
     pack_sources_kernel<Real, KID><<<blocks, 256, 0, stream>>>(Ns, r_src, n_src, v_src, pack);
     CU_TRY(cudaGetLastError());
   }
+  // coincidence probe (big problems only): lets the pair kernels skip the r2 == 0 mask when it cannot matter
+  int* must_mask = nullptr;
+  unsigned long long* table = nullptr;
+  int n_probe_launches = 0;
+  if (g.opt.probe_min_pairs > 0 && (double)Ns * (double)Nt >= (double)g.opt.probe_min_pairs) {
+    uint64_t slots = 1024;
+    while (slots < 2 * (uint64_t)Ns) slots <<= 1;
+    CU_TRY(cudaMallocAsync((void**)&table, (slots + 2) * sizeof(unsigned long long), stream));
+    CU_TRY(cudaMemsetAsync(table, 0, (slots + 2) * sizeof(unsigned long long), stream));
+    must_mask = reinterpret_cast<int*>(table + slots);
+    coincidence_insert_kernel<Real><<<(int)std::min<int64_t>((Ns + 255) / 256, 4096), 256, 0, stream>>>(Ns, r_src, table, slots - 1);
+    coincidence_probe_kernel<Real><<<(int)std::min<int64_t>((Nt + 255) / 256, 4096), 256, 0, stream>>>(Nt, r_trg, table, slots - 1, must_mask);
+    CU_TRY(cudaGetLastError());
+    n_probe_launches = 2;
+  }
   int rc;
   if (Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || g.opt.const_fp32))
-    rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, stream);
+    rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream);
   else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8)
-    rc = launch_eval_cfg<Real, KID, Tn::WIDE_T, Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, 8 * Tn::WIDE_TILE, 64);
+    rc = launch_eval_cfg<Real, KID, Tn::WIDE_T, Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, 8 * Tn::WIDE_TILE, 64);
   else if (Nt <= g.opt.few_max_targets)
-    rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, Tn::FEW_TILE, 1024);
+    rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, Tn::FEW_TILE, 1024);
   else
-    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, stream, 8 * Tn::TILE, 64);
+    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, 8 * Tn::TILE, 64);
+  if (table) cudaFreeAsync(table, stream);
+  tl.n_launches += n_probe_launches;
   if (rc) {
     cudaFreeAsync(pack, stream);
     return rc;
@@ -823,6 +847,7 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "few_max_targets")) g.opt.few_max_targets = value;
   else if (!strcmp(name, "wide_min_targets")) g.opt.wide_min_targets = value;
   else if (!strcmp(name, "const_fp32")) g.opt.const_fp32 = value;
+  else if (!strcmp(name, "probe_min_pairs")) g.opt.probe_min_pairs = value;
   else return fail("unknown option '%s'", name);
   return 0;
 }
