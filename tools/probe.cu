@@ -67,6 +67,51 @@ template <int MODE> void run(const char* what, int sms, const double* in, double
          n / (best * 1e-3) / sms / 1.965e9, 2 * n / (best * 1e-3) * 1e-12);
 }
 
+// FP32 operand probes: same modes as probe<> (0 shared m,c | 1 three distinct | 2 slot-A shared | 3 two distinct | 4 mul | 5 add | 6 slot-B shared)
+template <int MODE> __global__ void __launch_bounds__(256) probef(int iters, const double* __restrict__ in, double* out) {
+  constexpr int N = 12;
+  float a[N], b[N], c[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { a[i] = (float)in[i] + threadIdx.x; b[i] = (float)in[N + i] * 0.999f + threadIdx.x * 1e-6f; c[i] = (float)in[2 * N + i] * 1e-3f + threadIdx.x * 1e-7f; }
+  const float m = (float)in[40] + threadIdx.x * 1e-6f, cc = (float)in[41] + threadIdx.x * 1e-7f;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int i = 0; i < N; i++) {
+        if (MODE == 0) a[i] = fmaf(a[i], m, cc);
+        if (MODE == 1) a[i] = fmaf(b[i], c[i], a[i]);
+        if (MODE == 2) a[i] = fmaf(m, c[i], a[i]);
+        if (MODE == 3) a[i] = fmaf(b[i], b[i], a[i]);
+        if (MODE == 4) a[i] = a[i] * b[i];
+        if (MODE == 5) a[i] = a[i] + b[i];
+        if (MODE == 6) a[i] = fmaf(b[i], m, a[i]);
+        if (MODE == 7) a[i] = fmaf(a[i], 0.999f, 1e-6f);
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < N; i++) s += a[i] + b[i] + c[i];
+  if (s == -1.0f) out[0] = s;
+}
+template <int MODE> void runf(const char* what, int sms, const double* in, double* out, int threads, int blocks_per_sm) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int iters = 40000, blocks = sms * blocks_per_sm;
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; rep++) {
+    CK(cudaEventRecord(e0));
+    probef<MODE><<<blocks, threads>>>(iters, in, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    if (ms < best) best = ms;
+  }
+  const double n = (double)iters * 4 * 12 * blocks * threads;
+  printf("probef %-40s thr=%3d blk/SM=%d  %8.3f ms  %7.2f FP32-instr-lanes/clk/SM (@1.965GHz)\n", what, threads, blocks_per_sm, best, n / (best * 1e-3) / sms / 1.965e9);
+}
+
 // What does each auxiliary instruction of the pair loop cost the FP64 pipe?  24 two-operand DFMA per iteration plus
 // EXTRA: 0 nothing | 1 one MUFU.RSQ64H | 2 one MUFU.RSQ (f32) | 3 four ALU ops (add/compare/select/mov) | 4 two LDCU.64 | 5 all
 __constant__ double cprobe[1024];
@@ -188,6 +233,16 @@ int main() {
     run<7>("3 distinct + 2 int ops per DFMA", sms, in, out, threads, bps);
     run<8>("3 distinct + LDS.128 per 4 DFMA", sms, in, out, threads, bps);
     run<9>("fma(b,c,a) rotating dest", sms, in, out, threads, bps);
+  }
+  for (int bps : {2, 4}) {
+    runf<7>("ffma(a, imm, imm)", sms, in, out, 256, bps);
+    runf<0>("ffma(a, m, c) shared m,c", sms, in, out, 256, bps);
+    runf<1>("ffma(b_i, c_i, a_i) 3 distinct", sms, in, out, 256, bps);
+    runf<2>("ffma(m, c_i, a_i) slot-A shared", sms, in, out, 256, bps);
+    runf<6>("ffma(b_i, m, a_i) slot-B shared", sms, in, out, 256, bps);
+    runf<3>("ffma(b_i, b_i, a_i) 2 distinct", sms, in, out, 256, bps);
+    runf<4>("fmul(a_i, b_i)", sms, in, out, 256, bps);
+    runf<5>("fadd(a_i, b_i)", sms, in, out, 256, bps);
   }
   run4<0>("nothing", sms, in, out);
   run4<1>("1 MUFU.RSQ64H", sms, in, out);
