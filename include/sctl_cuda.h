@@ -15,7 +15,8 @@
  * All arrays are the reference's AoS Vector<Real> layouts (generic-kernel.txx:141,145-147,154):
  *   r_src[Ns*3], n_src[Ns*ND] (may be NULL when ND == 0), v_src[Ns*K0], r_trg[Nt*3], v_trg[Nt*K1],
  *   M[(Ns*K0) x (Nt*K1)] row-major with leading dimension ldM;  Real = double (real_bytes 8) or float (4).
- * (K0, K1, ND) per kernel id: FxU (1,1,0)  DxU (1,1,3)  FxdU (1,3,0)  Stokes FxU (3,3,0)  Stokes DxU (3,3,3).
+ * (K0, K1, ND) per kernel id: FxU (1,1,0)  DxU (1,1,3)  FxdU (1,3,0)  Stokes FxU (3,3,0)  Stokes DxU (3,3,3);
+ * ids 5-11 are listed with the enum below.
  *
  * Semantics kept from the reference:
  *   - Eval ACCUMULATES: v_trg += scale * sum_s K(x_t - x_s, n_s) f_s  (generic-kernel.txx:204-208).  The
@@ -48,7 +49,15 @@ enum sctl_cuda_kernel_id {
   SCTL_CUDA_LAPLACE3D_FXDU = 2, /* sctl::Laplace3D_FxdU  kernel_functions.hpp:81-123  */
   SCTL_CUDA_STOKES3D_FXU = 3,   /* sctl::Stokes3D_FxU    kernel_functions.hpp:125-178 */
   SCTL_CUDA_STOKES3D_DXU = 4,   /* sctl::Stokes3D_DxU    kernel_functions.hpp:180-218 */
-  SCTL_CUDA_NUM_KERNELS = 5
+  /* beyond the north-star five: the other non-Helmholtz kernels */
+  SCTL_CUDA_STOKES3D_FXT = 5,       /* sctl::Stokes3D_FxT      kernel_functions.hpp:220-254  (3,9,0) */
+  SCTL_CUDA_STOKES3D_FSXU = 6,      /* sctl::Stokes3D_FSxU     kernel_functions.hpp:256-324  (4,3,0) */
+  SCTL_CUDA_STOKES3D_FXUP = 7,      /* sctl::Stokes3D_FxUP     kernel_functions.hpp:326-364  (3,4,0) */
+  SCTL_CUDA_LAPLACE3D_FXD2U = 8,    /* sctl::Laplace3D_Fxd2U   kernel_functions.hpp:366-389  (1,9,0) */
+  SCTL_CUDA_LAPLACE3D_DXDU = 9,     /* sctl::Laplace3D_DxdU    kernel_functions.hpp:391-412  (1,3,3) */
+  SCTL_CUDA_BIOTSAVART3D_FXU = 10,  /* sctl::BiotSavart3D_FxU  kernel_functions.hpp:414-448  (3,3,0) */
+  SCTL_CUDA_BIOTSAVART3D_FXDU = 11, /* sctl::BiotSavart3D_FxdU kernel_functions.hpp:450-483  (3,9,0) */
+  SCTL_CUDA_NUM_KERNELS = 12
 };
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */

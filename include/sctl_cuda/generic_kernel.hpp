@@ -113,6 +113,13 @@ SCTL_CUDA_UKERNEL(Laplace3D_DxU, SCTL_CUDA_LAPLACE3D_DXU, "Laplace3D-DxU", 1, 1,
 SCTL_CUDA_UKERNEL(Laplace3D_FxdU, SCTL_CUDA_LAPLACE3D_FXDU, "Laplace3D-FxdU", 1, 3, 0, 11, -1, 4); // :81-110
 SCTL_CUDA_UKERNEL(Stokes3D_FxU, SCTL_CUDA_STOKES3D_FXU, "Stokes3D-FxU", 3, 3, 0, 23, 1, 8);        // :125-176
 SCTL_CUDA_UKERNEL(Stokes3D_DxU, SCTL_CUDA_STOKES3D_DXU, "Stokes3D-DxU", 3, 3, 3, 26, 3, 4);        // :180-217
+SCTL_CUDA_UKERNEL(Stokes3D_FxT, SCTL_CUDA_STOKES3D_FXT, "Stokes3D-FxT", 3, 9, 0, 39, -3, 4);       // :220-254
+SCTL_CUDA_UKERNEL(Stokes3D_FSxU, SCTL_CUDA_STOKES3D_FSXU, "Stokes3D-FSxU", 4, 3, 0, 26, 1, 8);     // :256-324
+SCTL_CUDA_UKERNEL(Stokes3D_FxUP, SCTL_CUDA_STOKES3D_FXUP, "Stokes3D-FxUP", 3, 4, 0, 26, 1, 8);     // :326-364
+SCTL_CUDA_UKERNEL(Laplace3D_Fxd2U, SCTL_CUDA_LAPLACE3D_FXD2U, "Laplace3D-Fxd2U", 1, 9, 0, 25, 1, 4);  // :366-389
+SCTL_CUDA_UKERNEL(Laplace3D_DxdU, SCTL_CUDA_LAPLACE3D_DXDU, "Laplace3D-DxdU", 1, 3, 3, 22, 1, 4);     // :391-412
+SCTL_CUDA_UKERNEL(BiotSavart3D_FxU, SCTL_CUDA_BIOTSAVART3D_FXU, "BiotSavart3D-FxU", 3, 3, 0, 15, 1, 4);      // :414-448
+SCTL_CUDA_UKERNEL(BiotSavart3D_FxdU, SCTL_CUDA_BIOTSAVART3D_FXDU, "BiotSavart3D-FxdU", 3, 9, 0, 51, -1, 4);  // :450-483
 #undef SCTL_CUDA_UKERNEL
 
 }  // namespace kernel_impl
@@ -163,6 +170,13 @@ using Laplace3D_DxU = GenericKernel<kernel_impl::Laplace3D_DxU>;
 using Laplace3D_FxdU = GenericKernel<kernel_impl::Laplace3D_FxdU>;
 using Stokes3D_FxU = GenericKernel<kernel_impl::Stokes3D_FxU>;
 using Stokes3D_DxU = GenericKernel<kernel_impl::Stokes3D_DxU>;
+using Stokes3D_FxT = GenericKernel<kernel_impl::Stokes3D_FxT>;
+using Stokes3D_FSxU = GenericKernel<kernel_impl::Stokes3D_FSxU>;
+using Stokes3D_FxUP = GenericKernel<kernel_impl::Stokes3D_FxUP>;
+using Laplace3D_Fxd2U = GenericKernel<kernel_impl::Laplace3D_Fxd2U>;
+using Laplace3D_DxdU = GenericKernel<kernel_impl::Laplace3D_DxdU>;
+using BiotSavart3D_FxU = GenericKernel<kernel_impl::BiotSavart3D_FxU>;
+using BiotSavart3D_FxdU = GenericKernel<kernel_impl::BiotSavart3D_FxdU>;
 
 }  // namespace sctl_cuda
 

@@ -18,9 +18,11 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
-KERNEL_IDS = {"Laplace3D_FxU": 0, "Laplace3D_DxU": 1, "Laplace3D_FxdU": 2, "Stokes3D_FxU": 3, "Stokes3D_DxU": 4}
+KERNEL_IDS = {"Laplace3D_FxU": 0, "Laplace3D_DxU": 1, "Laplace3D_FxdU": 2, "Stokes3D_FxU": 3, "Stokes3D_DxU": 4, "Stokes3D_FxT": 5, "Stokes3D_FSxU": 6,
+              "Stokes3D_FxUP": 7, "Laplace3D_Fxd2U": 8, "Laplace3D_DxdU": 9, "BiotSavart3D_FxU": 10, "BiotSavart3D_FxdU": 11}
 # (KDIM0, KDIM1, N_DIM): generic-kernel.hpp:22-41 applied to kernel_functions.hpp:43,72,92,136,191
-KERNEL_DIMS = {0: (1, 1, 0), 1: (1, 1, 3), 2: (1, 3, 0), 3: (3, 3, 0), 4: (3, 3, 3)}
+KERNEL_DIMS = {0: (1, 1, 0), 1: (1, 1, 3), 2: (1, 3, 0), 3: (3, 3, 0), 4: (3, 3, 3), 5: (3, 9, 0), 6: (4, 3, 0), 7: (3, 4, 0), 8: (1, 9, 0), 9: (1, 3, 3),
+               10: (3, 3, 0), 11: (3, 9, 0)}
 
 
 def _kid(kernel):

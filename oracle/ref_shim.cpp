@@ -64,6 +64,13 @@ template <class Real, class... A> int eval_ker(int kernel_id, int omp, int digit
     case 2: return eval_omp<Real, sctl::Laplace3D_FxdU>(omp, digits, a...);
     case 3: return eval_omp<Real, sctl::Stokes3D_FxU>(omp, digits, a...);
     case 4: return eval_omp<Real, sctl::Stokes3D_DxU>(omp, digits, a...);
+    case 5: return eval_omp<Real, sctl::Stokes3D_FxT>(omp, digits, a...);
+    case 6: return eval_omp<Real, sctl::Stokes3D_FSxU>(omp, digits, a...);
+    case 7: return eval_omp<Real, sctl::Stokes3D_FxUP>(omp, digits, a...);
+    case 8: return eval_omp<Real, sctl::Laplace3D_Fxd2U>(omp, digits, a...);
+    case 9: return eval_omp<Real, sctl::Laplace3D_DxdU>(omp, digits, a...);
+    case 10: return eval_omp<Real, sctl::BiotSavart3D_FxU>(omp, digits, a...);
+    case 11: return eval_omp<Real, sctl::BiotSavart3D_FxdU>(omp, digits, a...);
     default: return 1;
   }
 }
@@ -80,6 +87,13 @@ template <class Real, class... A> int kmat_ker(int kernel_id, int omp, int digit
     case 2: return kmat_omp<Real, sctl::Laplace3D_FxdU>(omp, digits, a...);
     case 3: return kmat_omp<Real, sctl::Stokes3D_FxU>(omp, digits, a...);
     case 4: return kmat_omp<Real, sctl::Stokes3D_DxU>(omp, digits, a...);
+    case 5: return kmat_omp<Real, sctl::Stokes3D_FxT>(omp, digits, a...);
+    case 6: return kmat_omp<Real, sctl::Stokes3D_FSxU>(omp, digits, a...);
+    case 7: return kmat_omp<Real, sctl::Stokes3D_FxUP>(omp, digits, a...);
+    case 8: return kmat_omp<Real, sctl::Laplace3D_Fxd2U>(omp, digits, a...);
+    case 9: return kmat_omp<Real, sctl::Laplace3D_DxdU>(omp, digits, a...);
+    case 10: return kmat_omp<Real, sctl::BiotSavart3D_FxU>(omp, digits, a...);
+    case 11: return kmat_omp<Real, sctl::BiotSavart3D_FxdU>(omp, digits, a...);
     default: return 1;
   }
 }
@@ -150,6 +164,13 @@ int sctl_ref_dims(int kernel_id, int* k0, int* k1, int* nd, int* flops, double* 
     case 2: fill(sctl::Laplace3D_FxdU()); return 0;
     case 3: fill(sctl::Stokes3D_FxU()); return 0;
     case 4: fill(sctl::Stokes3D_DxU()); return 0;
+    case 5: fill(sctl::Stokes3D_FxT()); return 0;
+    case 6: fill(sctl::Stokes3D_FSxU()); return 0;
+    case 7: fill(sctl::Stokes3D_FxUP()); return 0;
+    case 8: fill(sctl::Laplace3D_Fxd2U()); return 0;
+    case 9: fill(sctl::Laplace3D_DxdU()); return 0;
+    case 10: fill(sctl::BiotSavart3D_FxU()); return 0;
+    case 11: fill(sctl::BiotSavart3D_FxdU()); return 0;
     default: return 1;
   }
 }

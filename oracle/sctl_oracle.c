@@ -22,21 +22,35 @@
 #endif
 
 /* (KDIM0, KDIM1, N_DIM) deduced by generic-kernel.hpp:22-41 from each uKerMatrix signature. */
-static const int KDIMS[5][3] = {{1,1,0}, {1,1,3}, {1,3,0}, {3,3,0}, {3,3,3}};
+#define NKER 12
+static const int KDIMS[NKER][3] = {{1,1,0}, {1,1,3}, {1,3,0}, {3,3,0}, {3,3,3}, {3,9,0}, {4,3,0}, {3,4,0}, {1,9,0}, {1,3,3}, {3,3,0}, {3,9,0}};
 /* uKernel::FLOPS(): kernel_functions.hpp:37-39, 66-68, 86-88, 130-132, 185-187. */
-static const int KFLOPS[5] = {6, 14, 11, 23, 26};
-static const char* KNAMES[5] = {"Laplace3D-FxU", "Laplace3D-DxU", "Laplace3D-FxdU", "Stokes3D-FxU", "Stokes3D-DxU"};
+static const int KFLOPS[NKER] = {6, 14, 11, 23, 26, 39, 26, 26, 25, 22, 15, 51};  /* + :225-227, 261-263, 331-333, 371-373, 396-398, 419-421, 455-457 */
+static const char* KNAMES[NKER] = {"Laplace3D-FxU", "Laplace3D-DxU", "Laplace3D-FxdU", "Stokes3D-FxU", "Stokes3D-DxU", "Stokes3D-FxT", "Stokes3D-FSxU",
+                                   "Stokes3D-FxUP", "Laplace3D-Fxd2U", "Laplace3D-DxdU", "BiotSavart3D-FxU", "BiotSavart3D-FxdU"};
 
 #define ORACLE_PI 3.14159265358979323846264338327950288L
 
 /* uKerScaleFactor<Real>(): kernel_functions.hpp:40-42, 69-71, 89-91, 133-135, 188-190; evaluated in Real. */
 static double scale_factor_f64(int kid) {
   const double pi = (double)ORACLE_PI;
-  switch (kid) { case 0: case 1: return 1 / (4 * pi); case 2: return -1 / (4 * pi); case 3: return 1 / (8 * pi); default: return 3 / (4 * pi); }
+  switch (kid) {
+    case 0: case 1: case 8: case 9: case 10: return 1 / (4 * pi);
+    case 2: case 11: return -1 / (4 * pi);
+    case 3: case 6: case 7: return 1 / (8 * pi);
+    case 5: return -3 / (4 * pi);  /* kernel_functions.hpp:228-230 */
+    default: return 3 / (4 * pi);
+  }
 }
 static float scale_factor_f32(int kid) {
   const float pi = (float)ORACLE_PI;
-  switch (kid) { case 0: case 1: return 1 / (4 * pi); case 2: return -1 / (4 * pi); case 3: return 1 / (8 * pi); default: return 3 / (4 * pi); }
+  switch (kid) {
+    case 0: case 1: case 8: case 9: case 10: return 1 / (4 * pi);
+    case 2: case 11: return -1 / (4 * pi);
+    case 3: case 6: case 7: return 1 / (8 * pi);
+    case 5: return -3 / (4 * pi);  /* kernel_functions.hpp:228-230 */
+    default: return 3 / (4 * pi);
+  }
 }
 
 #define CAT_(a, b) a##b
@@ -59,7 +73,7 @@ static float scale_factor_f32(int kid) {
 #undef FN
 
 int oracle_eval(int kernel_id, int real_bytes, int omp, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg) {
-  if (kernel_id < 0 || kernel_id > 4) return 1;
+  if (kernel_id < 0 || kernel_id >= NKER) return 1;
   if (real_bytes == 8) eval_f64(kernel_id, omp, Ns, Nt, (const double*)r_src, (const double*)n_src, (const double*)v_src, (const double*)r_trg, (double*)v_trg);
   else if (real_bytes == 4) eval_f32(kernel_id, omp, Ns, Nt, (const float*)r_src, (const float*)n_src, (const float*)v_src, (const float*)r_trg, (float*)v_trg);
   else return 3;
@@ -67,7 +81,7 @@ int oracle_eval(int kernel_id, int real_bytes, int omp, int64_t Ns, int64_t Nt, 
 }
 
 int oracle_kernel_matrix(int kernel_id, int real_bytes, int omp, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM) {
-  if (kernel_id < 0 || kernel_id > 4) return 1;
+  if (kernel_id < 0 || kernel_id >= NKER) return 1;
   if (real_bytes == 8) kernel_matrix_f64(kernel_id, omp, Ns, Nt, (const double*)r_src, (const double*)n_src, (const double*)r_trg, (double*)M, ldM);
   else if (real_bytes == 4) kernel_matrix_f32(kernel_id, omp, Ns, Nt, (const float*)r_src, (const float*)n_src, (const float*)r_trg, (float*)M, ldM);
   else return 3;
@@ -91,7 +105,7 @@ int oracle_newton_iters(int real_bytes, int digits) {
 }
 
 int oracle_dims(int kernel_id, int* k0, int* k1, int* nd, int* flops, double* scale64, float* scale32, char* name, int name_len) {
-  if (kernel_id < 0 || kernel_id > 4) return 1;
+  if (kernel_id < 0 || kernel_id >= NKER) return 1;
   *k0 = KDIMS[kernel_id][0]; *k1 = KDIMS[kernel_id][1]; *nd = KDIMS[kernel_id][2]; *flops = KFLOPS[kernel_id];
   *scale64 = scale_factor_f64(kernel_id); *scale32 = scale_factor_f32(kernel_id);
   strncpy(name, KNAMES[kernel_id], (size_t)name_len - 1); name[name_len - 1] = 0;

@@ -8,6 +8,7 @@ static inline REAL FN(rsqrt_masked)(REAL r2) { return r2 > 0 ? (REAL)1 / SQRT(r2
 
 /* One source-target pair: dX = xt - xs (generic-kernel.txx:108-109), then the micro-kernel.
  * vt is the UNSCALED accumulator (scale applied once at the end, generic-kernel.txx:204-208). */
+static inline void FN(pair_matrix)(int kid, REAL* u, const REAL* r, const REAL* ns);
 static inline void FN(pair_apply)(int kid, REAL* vt, const REAL* xt, const REAL* xs, const REAL* ns, const REAL* f) {
   REAL r[3];
   for (int k = 0; k < 3; k++) r[k] = xt[k] - xs[k];
@@ -39,6 +40,38 @@ static inline void FN(pair_apply)(int kid, REAL* vt, const REAL* xt, const REAL*
       const REAL t = (f[0]*r[0] + f[1]*r[1] + f[2]*r[2]) * rdotn_rinv5;
       for (int i = 0; i < 3; i++) vt[i] += r[i] * t;
     } break;
+    case 5: { /* Stokes3D_FxT fused apply: kernel_functions.hpp:241-252 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL rinv5 = rinv2 * rinv2 * rinv;
+      const REAL fdotr_rinv5 = (f[0]*r[0] + f[1]*r[1] + f[2]*r[2]) * rinv5;
+      for (int i = 0; i < 3; i++) {
+        const REAL ri = r[i] * fdotr_rinv5;
+        for (int j = 0; j < 3; j++) vt[i*3+j] += ri * r[j];
+      }
+    } break;
+    case 6: { /* Stokes3D_FSxU fused apply: kernel_functions.hpp:311-321 */
+      const REAL rinv3 = rinv * rinv * rinv;
+      const REAL t = (f[0]*r[0] + f[1]*r[1] + f[2]*r[2] + f[3]) * rinv3;
+      for (int i = 0; i < 3; i++) vt[i] += f[i]*rinv + r[i]*t;
+    } break;
+    case 7: { /* Stokes3D_FxUP fused apply: kernel_functions.hpp:351-362 */
+      const REAL rinv3 = rinv * rinv * rinv;
+      const REAL t = (f[0]*r[0] + f[1]*r[1] + f[2]*r[2]) * rinv3;
+      for (int i = 0; i < 3; i++) vt[i] += f[i]*rinv + r[i]*t;
+      vt[3] += t;
+    } break;
+    case 8: case 9: case 11: { /* no fused apply: uKerMatrix then FMA, generic-kernel.txx:113-119 */
+      REAL u[27];
+      const int K0 = KDIMS[kid][0], K1 = KDIMS[kid][1];
+      FN(pair_matrix)(kid, u, r, ns);
+      for (int k0 = 0; k0 < K0; k0++) for (int k1 = 0; k1 < K1; k1++) vt[k1] = u[k0*K1+k1] * f[k0] + vt[k1];
+    } break;
+    case 10: { /* BiotSavart3D_FxU fused apply: kernel_functions.hpp:436-447 */
+      const REAL rinv3 = rinv * rinv * rinv;
+      vt[0] += (f[1]*r[2] - r[1]*f[2]) * rinv3;
+      vt[1] += (f[2]*r[0] - r[2]*f[0]) * rinv3;
+      vt[2] += (f[0]*r[1] - r[0]*f[1]) * rinv3;
+    } break;
   }
 }
 
@@ -68,6 +101,56 @@ static inline void FN(pair_matrix)(int kid, REAL* u, const REAL* r, const REAL* 
       const REAL rdotn_rinv5 = (r[0]*ns[0] + r[1]*ns[1] + r[2]*ns[2]) * rinv5;
       for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) u[i*3+j] = r[i]*r[j]*rdotn_rinv5;
     } break;
+    case 5: { /* Stokes3D_FxT: kernel_functions.hpp:230-239 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL rinv5 = rinv2 * rinv2 * rinv;
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) u[i*9+j*3+k] = r[i]*r[j]*r[k]*rinv5;
+    } break;
+    case 6: { /* Stokes3D_FSxU: kernel_functions.hpp:267-279 */
+      const REAL rinv3 = rinv * rinv * rinv;
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) u[i*3+j] = (i == j ? rinv : (REAL)0) + r[i]*r[j]*rinv3;
+      for (int j = 0; j < 3; j++) u[9+j] = r[j]*rinv3;
+    } break;
+    case 7: { /* Stokes3D_FxUP: kernel_functions.hpp:337-349 */
+      const REAL rinv3 = rinv * rinv * rinv;
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) u[i*4+j] = (i == j ? rinv : (REAL)0) + r[i]*r[j]*rinv3;
+      for (int i = 0; i < 3; i++) u[i*4+3] = r[i]*rinv3;
+    } break;
+    case 8: { /* Laplace3D_Fxd2U: kernel_functions.hpp:376-388 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL rinv3 = rinv * rinv2;
+      const REAL t5 = (REAL)3 * rinv3 * rinv2;
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) u[i*3+j] = t5 * r[i] * r[j] - (i == j ? rinv3 : (REAL)0);
+    } break;
+    case 9: { /* Laplace3D_DxdU: kernel_functions.hpp:402-411 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL rinv3 = rinv * rinv2;
+      const REAL rdotn = r[0]*ns[0] + r[1]*ns[1] + r[2]*ns[2];
+      const REAL t5 = (REAL)3 * rdotn * rinv3 * rinv2;
+      for (int i = 0; i < 3; i++) u[i] = ns[i] * rinv3 - r[i] * t5;
+    } break;
+    case 10: { /* BiotSavart3D_FxU: kernel_functions.hpp:425-433 */
+      const REAL rinv3 = rinv * rinv * rinv;
+      u[0] = 0;           u[1] = -r[2]*rinv3; u[2] =  r[1]*rinv3;
+      u[3] =  r[2]*rinv3; u[4] = 0;           u[5] = -r[0]*rinv3;
+      u[6] = -r[1]*rinv3; u[7] =  r[0]*rinv3; u[8] = 0;
+    } break;
+    case 11: { /* BiotSavart3D_FxdU: kernel_functions.hpp:460-482; u[k0][k1] at u[k0*9+k1] */
+      const REAL rinv2 = rinv * rinv;
+      const REAL rinv3 = rinv * rinv2;
+      const REAL t5 = (REAL)3 * rinv3 * rinv2;
+      const REAL Z = 0;
+      REAL (*U)[9] = (REAL (*)[9])u;
+      U[0][0] =                    Z; U[1][0] =         t5*r[2]*r[0]; U[2][0] =        -t5*r[1]*r[0];
+      U[0][1] =                    Z; U[1][1] =         t5*r[2]*r[1]; U[2][1] =  rinv3 -t5*r[1]*r[1];
+      U[0][2] =                    Z; U[1][2] = -rinv3 +t5*r[2]*r[2]; U[2][2] =        -t5*r[1]*r[2];
+      U[0][3] =        -t5*r[2]*r[0]; U[1][3] =                    Z; U[2][3] = -rinv3 +t5*r[0]*r[0];
+      U[0][4] =        -t5*r[2]*r[1]; U[1][4] =                    Z; U[2][4] =         t5*r[0]*r[1];
+      U[0][5] =  rinv3 -t5*r[2]*r[2]; U[1][5] =                    Z; U[2][5] =         t5*r[0]*r[2];
+      U[0][6] =         t5*r[1]*r[0]; U[1][6] =  rinv3 -t5*r[0]*r[0]; U[2][6] =                    Z;
+      U[0][7] = -rinv3 +t5*r[1]*r[1]; U[1][7] =        -t5*r[0]*r[1]; U[2][7] =                    Z;
+      U[0][8] =         t5*r[1]*r[2]; U[1][8] =        -t5*r[0]*r[2]; U[2][8] =                    Z;
+    } break;
   }
 }
 
@@ -79,7 +162,7 @@ static void FN(eval)(int kid, int omp, int64_t Ns, int64_t Nt, const REAL* r_src
   const REAL scale = (REAL)FN(scale_factor)(kid);
   #pragma omp parallel for schedule(static) if (omp)
   for (int64_t t = 0; t < Nt; t++) {
-    REAL acc[3] = {0, 0, 0};
+    REAL acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t s = 0; s < Ns; s++)
       FN(pair_apply)(kid, acc, r_trg + t*3, r_src + s*3, ND ? n_src + s*ND : (const REAL*)0, v_src + s*K0);
     for (int k = 0; k < K1; k++) v_trg[t*K1 + k] += acc[k] * scale;
@@ -94,7 +177,7 @@ static void FN(kernel_matrix)(int kid, int omp, int64_t Ns, int64_t Nt, const RE
   #pragma omp parallel for schedule(static) if (omp)
   for (int64_t s = 0; s < Ns; s++) {
     for (int64_t t = 0; t < Nt; t++) {
-      REAL r[3], u[9];
+      REAL r[3], u[27];
       for (int k = 0; k < 3; k++) r[k] = r_trg[t*3+k] - r_src[s*3+k];
       FN(pair_matrix)(kid, u, r, ND ? n_src + s*ND : (const REAL*)0);
       for (int k0 = 0; k0 < K0; k0++) for (int k1 = 0; k1 < K1; k1++) M[(s*K0+k0)*ldM + t*K1+k1] = u[k0*K1+k1] * scale;

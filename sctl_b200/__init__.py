@@ -19,7 +19,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsctl_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sctl_cuda.h")
 
-KERNEL_IDS = {"Laplace3D_FxU": 0, "Laplace3D_DxU": 1, "Laplace3D_FxdU": 2, "Stokes3D_FxU": 3, "Stokes3D_DxU": 4}
+KERNEL_IDS = {"Laplace3D_FxU": 0, "Laplace3D_DxU": 1, "Laplace3D_FxdU": 2, "Stokes3D_FxU": 3, "Stokes3D_DxU": 4, "Stokes3D_FxT": 5, "Stokes3D_FSxU": 6,
+              "Stokes3D_FxUP": 7, "Laplace3D_Fxd2U": 8, "Laplace3D_DxdU": 9, "BiotSavart3D_FxU": 10, "BiotSavart3D_FxdU": 11}
 
 _lib = None
 
@@ -192,6 +193,9 @@ class GenericKernel:
     _META = {
         0: (1, 1, 0, 6, "Laplace3D-FxU"), 1: (1, 1, 3, 14, "Laplace3D-DxU"), 2: (1, 3, 0, 11, "Laplace3D-FxdU"),
         3: (3, 3, 0, 23, "Stokes3D-FxU"), 4: (3, 3, 3, 26, "Stokes3D-DxU"),
+        # kernel_functions.hpp:220-483
+        5: (3, 9, 0, 39, "Stokes3D-FxT"), 6: (4, 3, 0, 26, "Stokes3D-FSxU"), 7: (3, 4, 0, 26, "Stokes3D-FxUP"), 8: (1, 9, 0, 25, "Laplace3D-Fxd2U"),
+        9: (1, 3, 3, 22, "Laplace3D-DxdU"), 10: (3, 3, 0, 15, "BiotSavart3D-FxU"), 11: (3, 9, 0, 51, "BiotSavart3D-FxdU"),
     }
 
     def __init__(self, kernel):
@@ -226,7 +230,8 @@ class GenericKernel:
     def uKerScaleFactor(self, dtype=np.float64):
         pi = dtype(np.pi)
         one = dtype(1)
-        return {0: one / (4 * pi), 1: one / (4 * pi), 2: -one / (4 * pi), 3: one / (8 * pi), 4: dtype(3) / (4 * pi)}[self.kernel_id]
+        return {0: one / (4 * pi), 1: one / (4 * pi), 2: -one / (4 * pi), 3: one / (8 * pi), 4: dtype(3) / (4 * pi), 5: dtype(-3) / (4 * pi), 6: one / (8 * pi),
+                7: one / (8 * pi), 8: one / (4 * pi), 9: one / (4 * pi), 10: one / (4 * pi), 11: -one / (4 * pi)}[self.kernel_id]
 
     def _arrays(self, r_trg, r_src, n_src, v_src, dtype, need_v=True):
         r_trg = np.ascontiguousarray(r_trg, dtype=dtype).reshape(-1)
@@ -283,5 +288,11 @@ Laplace3D_DxU = GenericKernel("Laplace3D_DxU")
 Laplace3D_FxdU = GenericKernel("Laplace3D_FxdU")
 Stokes3D_FxU = GenericKernel("Stokes3D_FxU")
 Stokes3D_DxU = GenericKernel("Stokes3D_DxU")
-KERNELS = {"Laplace3D_FxU": Laplace3D_FxU, "Laplace3D_DxU": Laplace3D_DxU, "Laplace3D_FxdU": Laplace3D_FxdU, "Stokes3D_FxU": Stokes3D_FxU,
-           "Stokes3D_DxU": Stokes3D_DxU}
+Stokes3D_FxT = GenericKernel("Stokes3D_FxT")
+Stokes3D_FSxU = GenericKernel("Stokes3D_FSxU")
+Stokes3D_FxUP = GenericKernel("Stokes3D_FxUP")
+Laplace3D_Fxd2U = GenericKernel("Laplace3D_Fxd2U")
+Laplace3D_DxdU = GenericKernel("Laplace3D_DxdU")
+BiotSavart3D_FxU = GenericKernel("BiotSavart3D_FxU")
+BiotSavart3D_FxdU = GenericKernel("BiotSavart3D_FxdU")
+KERNELS = {name: GenericKernel(name) for name in KERNEL_IDS}

@@ -64,8 +64,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // ------------------------------------------------------------------------------------------------
 // Source packing:  AoS r_src | n_src | v_src  ->  one record per source
-//   FxU, FxdU : [x y z f]                 Stokes FxU : [x y z fx fy fz]
-//   Laplace DxU: [x y z f*nx f*ny f*nz]   Stokes DxU : [x y z fx fy fz nx ny nz]   (+ zero padding to 16 B)
+//   FxU, FxdU, Fxd2U : [x y z f]          Stokes FxU/FxT/FxUP, BiotSavart : [x y z fx fy fz]
+//   Laplace DxU/DxdU: [x y z f*nx f*ny f*nz]   Stokes DxU : [x y z f n]   Stokes FSxU : [x y z f0..f3]   (+ zero padding to 16 B)
 // O(Ns) work in front of an O(Ns*Nt) kernel; it buys 16-byte alignment for arbitrary caller pointers,
 // one bulk copy per tile, and one FP64 instruction per pair for Laplace DxU.
 // ------------------------------------------------------------------------------------------------
@@ -80,7 +80,7 @@ __global__ void pack_sources_kernel(int64_t Ns, const Real* __restrict__ r_src, 
     for (int k = 0; k < REC; k++) rec[k] = 0;
 #pragma unroll
     for (int k = 0; k < 3; k++) rec[k] = r_src[s * 3 + k];
-    if (KID == LAPLACE3D_DXU) {
+    if (KID == LAPLACE3D_DXU || KID == LAPLACE3D_DXDU) {  // double-layer Laplace kernels are linear in f*n
       const Real f = v_src[s];
 #pragma unroll
       for (int k = 0; k < 3; k++) rec[3 + k] = f * n_src[s * 3 + k];

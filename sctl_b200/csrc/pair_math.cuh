@@ -14,7 +14,12 @@
 
 namespace sctl_cuda {
 
-enum : int { LAPLACE3D_FXU = 0, LAPLACE3D_DXU = 1, LAPLACE3D_FXDU = 2, STOKES3D_FXU = 3, STOKES3D_DXU = 4, NUM_KERNELS = 5 };
+// 0-4: the north-star kernels.  5-11: the other non-Helmholtz kernels of kernel_functions.hpp.
+enum : int {
+  LAPLACE3D_FXU = 0, LAPLACE3D_DXU = 1, LAPLACE3D_FXDU = 2, STOKES3D_FXU = 3, STOKES3D_DXU = 4,
+  STOKES3D_FXT = 5, STOKES3D_FSXU = 6, STOKES3D_FXUP = 7, LAPLACE3D_FXD2U = 8, LAPLACE3D_DXDU = 9, BIOTSAVART3D_FXU = 10, BIOTSAVART3D_FXDU = 11,
+  NUM_KERNELS = 12
+};
 
 // How far the seed is refined; chosen on the host from `digits` (see rsq_mode_for_digits()).
 enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
@@ -74,6 +79,14 @@ template <> struct KerTraits<LAPLACE3D_DXU>  { static constexpr int K0 = 1, K1 =
 template <> struct KerTraits<LAPLACE3D_FXDU> { static constexpr int K0 = 1, K1 = 3, ND = 0, PACK = 4, FLOPS = 11, F_ALG = 18; };
 template <> struct KerTraits<STOKES3D_FXU>   { static constexpr int K0 = 3, K1 = 3, ND = 0, PACK = 6, FLOPS = 23, F_ALG = 29; };
 template <> struct KerTraits<STOKES3D_DXU>   { static constexpr int K0 = 3, K1 = 3, ND = 3, PACK = 9, FLOPS = 26, F_ALG = 30; };
+// kernel_functions.hpp:220-483.  F_ALG here = flop count of the fused device formulation below (FMA = 2, rsqrt = 1).
+template <> struct KerTraits<STOKES3D_FXT>      { static constexpr int K0 = 3, K1 = 9, ND = 0, PACK = 6, FLOPS = 39, F_ALG = 39; };
+template <> struct KerTraits<STOKES3D_FSXU>     { static constexpr int K0 = 4, K1 = 3, ND = 0, PACK = 7, FLOPS = 26, F_ALG = 30; };
+template <> struct KerTraits<STOKES3D_FXUP>     { static constexpr int K0 = 3, K1 = 4, ND = 0, PACK = 6, FLOPS = 26, F_ALG = 31; };
+template <> struct KerTraits<LAPLACE3D_FXD2U>   { static constexpr int K0 = 1, K1 = 9, ND = 0, PACK = 4, FLOPS = 25, F_ALG = 38; };
+template <> struct KerTraits<LAPLACE3D_DXDU>    { static constexpr int K0 = 1, K1 = 3, ND = 3, PACK = 6, FLOPS = 22, F_ALG = 30; };
+template <> struct KerTraits<BIOTSAVART3D_FXU>  { static constexpr int K0 = 3, K1 = 3, ND = 0, PACK = 6, FLOPS = 15, F_ALG = 26; };
+template <> struct KerTraits<BIOTSAVART3D_FXDU> { static constexpr int K0 = 3, K1 = 9, ND = 0, PACK = 6, FLOPS = 51, F_ALG = 52; };
 
 // Reals per record, padded so that every record is a whole number of 16-byte words (LDS.128 / bulk-copy unit).
 template <class Real, int KID> struct RecTraits {
@@ -89,6 +102,13 @@ __host__ inline KernelInfo kernel_info(int kid) {
     case LAPLACE3D_FXDU: return {1, 3, 0, 11, 18, "Laplace3D-FxdU"};
     case STOKES3D_FXU:   return {3, 3, 0, 23, 29, "Stokes3D-FxU"};
     case STOKES3D_DXU:   return {3, 3, 3, 26, 30, "Stokes3D-DxU"};
+    case STOKES3D_FXT:      return {3, 9, 0, 39, 39, "Stokes3D-FxT"};
+    case STOKES3D_FSXU:     return {4, 3, 0, 26, 30, "Stokes3D-FSxU"};
+    case STOKES3D_FXUP:     return {3, 4, 0, 26, 31, "Stokes3D-FxUP"};
+    case LAPLACE3D_FXD2U:   return {1, 9, 0, 25, 38, "Laplace3D-Fxd2U"};
+    case LAPLACE3D_DXDU:    return {1, 3, 3, 22, 30, "Laplace3D-DxdU"};
+    case BIOTSAVART3D_FXU:  return {3, 3, 0, 15, 26, "BiotSavart3D-FxU"};
+    case BIOTSAVART3D_FXDU: return {3, 9, 0, 51, 52, "BiotSavart3D-FxdU"};
     default:             return {0, 0, 0, 0, 0, nullptr};
   }
 }
@@ -97,10 +117,11 @@ __host__ inline KernelInfo kernel_info(int kid) {
 template <class Real> __host__ __device__ inline Real scale_factor(int kid) {
   const Real pi = (Real)3.14159265358979323846264338327950288L;
   switch (kid) {
-    case LAPLACE3D_FXU: case LAPLACE3D_DXU: return 1 / (4 * pi);
-    case LAPLACE3D_FXDU: return -1 / (4 * pi);
-    case STOKES3D_FXU: return 1 / (8 * pi);
-    default: return 3 / (4 * pi);
+    case LAPLACE3D_FXU: case LAPLACE3D_DXU: case LAPLACE3D_FXD2U: case LAPLACE3D_DXDU: case BIOTSAVART3D_FXU: return 1 / (4 * pi);
+    case LAPLACE3D_FXDU: case BIOTSAVART3D_FXDU: return -1 / (4 * pi);
+    case STOKES3D_FXU: case STOKES3D_FSXU: case STOKES3D_FXUP: return 1 / (8 * pi);
+    case STOKES3D_FXT: return -3 / (4 * pi);
+    default: return 3 / (4 * pi);  // Stokes3D_DxU
   }
 }
 
@@ -160,6 +181,103 @@ template <class Real> struct PairApply<STOKES3D_DXU, Real> {
   }
 };
 
+
+// ---- the other non-Helmholtz kernels (kernel_functions.hpp:220-483) ----
+// Stokes3D_FxT: v_ij += r_i r_j (f.r) rinv^5                    (fused apply, :241-252)
+template <class Real> struct PairApply<STOKES3D_FXT, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv5 = (rinv2 * rinv2) * rinv;
+    const Real t = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) * rinv5;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const Real a = dx[i] * t;
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[i * 3 + j] = fma(a, dx[j], acc[i * 3 + j]);
+    }
+  }
+};
+// Stokes3D_FSxU: v_i += f_i rinv + r_i (f.r + f_3) rinv^3        (fused apply, :311-321)
+template <class Real> struct PairApply<STOKES3D_FSXU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    // one source value per instruction: a DFMA can take a single uniform-register operand (constant-bank path)
+    const Real c = (fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) + s[6]) * rinv2;
+    acc[0] = fma(rinv, fma(dx[0], c, s[3]), acc[0]);
+    acc[1] = fma(rinv, fma(dx[1], c, s[4]), acc[1]);
+    acc[2] = fma(rinv, fma(dx[2], c, s[5]), acc[2]);
+  }
+};
+// Stokes3D_FxUP: velocity as Stokes3D_FxU, pressure v_3 += (f.r) rinv^3   (fused apply, :351-362)
+template <class Real> struct PairApply<STOKES3D_FXUP, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[4], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    const Real c = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) * rinv2;
+    acc[0] = fma(rinv, fma(dx[0], c, s[3]), acc[0]);
+    acc[1] = fma(rinv, fma(dx[1], c, s[4]), acc[1]);
+    acc[2] = fma(rinv, fma(dx[2], c, s[5]), acc[2]);
+    acc[3] = fma(rinv, c, acc[3]);
+  }
+};
+// Laplace3D_Fxd2U: v_ij += f (3 r_i r_j rinv^5 - delta_ij rinv^3)        (uKerMatrix + FMA, :376-388)
+template <class Real> struct PairApply<LAPLACE3D_FXD2U, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    const Real g = (rinv2 * rinv) * s[3];
+    const Real h = (g * rinv2) * (Real)3;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const Real a = dx[i] * h;
+#pragma unroll
+      for (int j = 0; j < 3; j++) acc[i * 3 + j] = fma(a, dx[j], acc[i * 3 + j]);
+      acc[i * 3 + i] -= g;
+    }
+  }
+};
+// Laplace3D_DxdU: v_i += f (n_i rinv^3 - 3 r_i (r.n) rinv^5); the record carries g = f*n     (:402-411)
+template <class Real> struct PairApply<LAPLACE3D_DXDU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv3 = rinv2 * rinv;
+    const Real c = (fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) * rinv2) * (Real)3;
+    acc[0] = fma(rinv3, fma(-dx[0], c, s[3]), acc[0]);
+    acc[1] = fma(rinv3, fma(-dx[1], c, s[4]), acc[1]);
+    acc[2] = fma(rinv3, fma(-dx[2], c, s[5]), acc[2]);
+  }
+};
+// BiotSavart3D_FxU: v += (f x r) rinv^3                                  (fused apply, :436-447)
+template <class Real> struct PairApply<BIOTSAVART3D_FXU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv3 = rinv * rinv * rinv;
+    acc[0] = fma(fma(s[4], dx[2], -(dx[1] * s[5])), rinv3, acc[0]);
+    acc[1] = fma(fma(s[5], dx[0], -(dx[2] * s[3])), rinv3, acc[1]);
+    acc[2] = fma(fma(s[3], dx[1], -(dx[0] * s[4])), rinv3, acc[2]);
+  }
+};
+// BiotSavart3D_FxdU: v_ab += eps_abk f_k rinv^3 + 3 (f x r)_a r_b rinv^5   (uKerMatrix + FMA, :460-482; the 3 x 9
+// block is the negated gradient of the FxU block, its sign lives in the scale factor)
+template <class Real> struct PairApply<BIOTSAVART3D_FXDU, Real> {
+  static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const Real* s) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv3 = rinv2 * rinv;
+    const Real t5 = (rinv3 * rinv2) * (Real)3;
+    Real c[3];
+    c[0] = fma(s[4], dx[2], -(dx[1] * s[5]));
+    c[1] = fma(s[5], dx[0], -(dx[2] * s[3]));
+    c[2] = fma(s[3], dx[1], -(dx[0] * s[4]));
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const Real ca = c[a] * t5;
+#pragma unroll
+      for (int b = 0; b < 3; b++) acc[a * 3 + b] = fma(ca, dx[b], acc[a * 3 + b]);
+    }
+    const Real g0 = s[3] * rinv3, g1 = s[4] * rinv3, g2 = s[5] * rinv3;
+    acc[1] += g2; acc[2] -= g1;
+    acc[3] -= g2; acc[5] += g0;
+    acc[6] += g1; acc[7] -= g0;
+  }
+};
+
 // One source-target pair, starting from coordinates.
 template <int KID, int RSQ, bool MASK = true, class Real>
 __device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], const Real (&xt)[3], const Real* s) {
@@ -212,6 +330,101 @@ template <class Real> struct PairMatrix<STOKES3D_DXU, Real> {
 #pragma unroll
       for (int j = 0; j < 3; j++) u[i * 3 + j] = a * dx[j];
     }
+  }
+};
+
+
+template <class Real> struct PairMatrix<STOKES3D_FXT, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv5 = (rinv2 * rinv2) * rinv;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const Real a = (dx[i] * dx[j]) * rinv5;
+#pragma unroll
+        for (int k = 0; k < 3; k++) u[i * 9 + j * 3 + k] = a * dx[k];
+      }
+  }
+};
+template <class Real> struct PairMatrix<STOKES3D_FSXU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv3 = rinv * rinv * rinv;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const Real a = dx[i] * rinv3;
+#pragma unroll
+      for (int j = 0; j < 3; j++) u[i * 3 + j] = (i == j) ? fma(a, dx[j], rinv) : a * dx[j];
+      u[9 + i] = a;
+    }
+  }
+};
+template <class Real> struct PairMatrix<STOKES3D_FXUP, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv3 = rinv * rinv * rinv;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const Real a = dx[i] * rinv3;
+#pragma unroll
+      for (int j = 0; j < 3; j++) u[i * 4 + j] = (i == j) ? fma(a, dx[j], rinv) : a * dx[j];
+      u[i * 4 + 3] = a;
+    }
+  }
+};
+template <class Real> struct PairMatrix<LAPLACE3D_FXD2U, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv3 = rinv2 * rinv;
+    const Real t5 = (rinv3 * rinv2) * (Real)3;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const Real a = dx[i] * t5;
+#pragma unroll
+      for (int j = 0; j < 3; j++) u[i * 3 + j] = (i == j) ? fma(a, dx[j], -rinv3) : a * dx[j];
+    }
+  }
+};
+template <class Real> struct PairMatrix<LAPLACE3D_DXDU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv3 = rinv2 * rinv;
+    const Real t5 = ((fma(dx[2], n[2], fma(dx[1], n[1], dx[0] * n[0])) * rinv2) * rinv3) * (Real)3;
+#pragma unroll
+    for (int i = 0; i < 3; i++) u[i] = fma(-dx[i], t5, n[i] * rinv3);
+  }
+};
+template <class Real> struct PairMatrix<BIOTSAVART3D_FXU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv3 = rinv * rinv * rinv;
+    const Real a0 = dx[0] * rinv3, a1 = dx[1] * rinv3, a2 = dx[2] * rinv3;
+    u[0] = 0;   u[1] = -a2; u[2] = a1;
+    u[3] = a2;  u[4] = 0;   u[5] = -a0;
+    u[6] = -a1; u[7] = a0;  u[8] = 0;
+  }
+};
+template <class Real> struct PairMatrix<BIOTSAVART3D_FXDU, Real> {
+  static __device__ __forceinline__ void run(Real* u, const Real (&dx)[3], Real rinv, const Real* n) {
+    const Real rinv2 = rinv * rinv;
+    const Real rinv3 = rinv2 * rinv;
+    const Real t5 = (rinv3 * rinv2) * (Real)3;
+    // u[k0][3a+b] = -eps_{a k0 b} rinv3 + t5 (eps_{a k0 c} r_c) r_b
+#pragma unroll
+    for (int k0 = 0; k0 < 3; k0++)
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        // e_c = eps_{a k0 c} r_c : nonzero only for c = 3 - a - k0 when a != k0
+        const int c = 3 - a - k0;
+        const bool nz = (a != k0);
+        const Real sgn = nz ? ((((k0 - a + 3) % 3) == 1) ? (Real)1 : (Real)-1) : (Real)0;  // eps_{a k0 c}
+        const Real e = nz ? sgn * dx[c < 3 ? c : 0] : (Real)0;
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          Real val = (t5 * e) * dx[b];
+          if (nz && b == c) val -= sgn * rinv3;  // -eps_{a k0 b} rinv3
+          u[k0 * 9 + a * 3 + b] = val;
+        }
+      }
   }
 };
 

@@ -339,8 +339,8 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
   int rc;
   if (Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || g.opt.const_fp32))
     rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream);
-  else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8)
-    rc = launch_eval_cfg<Real, KID, Tn::WIDE_T, Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, 8 * Tn::WIDE_TILE, 64);
+  else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8 && KerTraits<KID>::K1 <= 4)  // 9 accumulators x 4 targets would spill
+    rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, 8 * Tn::WIDE_TILE, 64);
   else if (Nt <= g.opt.few_max_targets)
     rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, Tn::FEW_TILE, 1024);
   else
@@ -377,6 +377,13 @@ int eval_device_r(int dev, int kid, int digits, int64_t Ns, int64_t Nt, const vo
     SCTL_CUDA_CASE(LAPLACE3D_FXDU)
     SCTL_CUDA_CASE(STOKES3D_FXU)
     SCTL_CUDA_CASE(STOKES3D_DXU)
+    SCTL_CUDA_CASE(STOKES3D_FXT)
+    SCTL_CUDA_CASE(STOKES3D_FSXU)
+    SCTL_CUDA_CASE(STOKES3D_FXUP)
+    SCTL_CUDA_CASE(LAPLACE3D_FXD2U)
+    SCTL_CUDA_CASE(LAPLACE3D_DXDU)
+    SCTL_CUDA_CASE(BIOTSAVART3D_FXU)
+    SCTL_CUDA_CASE(BIOTSAVART3D_FXDU)
     default: return fail("unknown kernel id %d", kid);
   }
 #undef SCTL_CUDA_CASE
@@ -430,6 +437,13 @@ int kmat_device_r(int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src
     SCTL_CUDA_CASE(LAPLACE3D_FXDU)
     SCTL_CUDA_CASE(STOKES3D_FXU)
     SCTL_CUDA_CASE(STOKES3D_DXU)
+    SCTL_CUDA_CASE(STOKES3D_FXT)
+    SCTL_CUDA_CASE(STOKES3D_FSXU)
+    SCTL_CUDA_CASE(STOKES3D_FXUP)
+    SCTL_CUDA_CASE(LAPLACE3D_FXD2U)
+    SCTL_CUDA_CASE(LAPLACE3D_DXDU)
+    SCTL_CUDA_CASE(BIOTSAVART3D_FXU)
+    SCTL_CUDA_CASE(BIOTSAVART3D_FXDU)
     default: return fail("unknown kernel id %d", kid);
   }
 #undef SCTL_CUDA_CASE

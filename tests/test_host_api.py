@@ -57,7 +57,7 @@ def test_kernel_info_matches_oracle_and_python_mirror(sbm, port):
         assert abs(float(K.uKerScaleFactor(np.float32)) - d["scale32"]) < 1e-7
     assert sbm.kernel_info(3)["f_alg"] == 29  # Stokes3D_FxU algorithmic flop per pair
     with pytest.raises(sbm.SctlCudaError):
-        sbm.kernel_info(7)
+        sbm.kernel_info(12)
 
 
 def test_planner_fills_waves(sbm):
@@ -98,7 +98,7 @@ def test_precondition_violations_raise(sbm):
     L = sbm.load_library()
     z = np.zeros(8)
     p = z.ctypes.data_as(ctypes.c_void_p)
-    assert L.sctl_cuda_eval(9, 8, -1, 1, 1, p, p, p, p, p, None, 0) != 0 and b"kernel id" in L.sctl_cuda_last_error()
+    assert L.sctl_cuda_eval(99, 8, -1, 1, 1, p, p, p, p, p, None, 0) != 0 and b"kernel id" in L.sctl_cuda_last_error()
     assert L.sctl_cuda_eval(0, 2, -1, 1, 1, p, p, p, p, p, None, 0) != 0 and b"real_bytes" in L.sctl_cuda_last_error()
     assert L.sctl_cuda_eval(0, 8, -1, -1, 1, p, p, p, p, p, None, 0) != 0 and b"negative" in L.sctl_cuda_last_error()
 
