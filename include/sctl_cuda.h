@@ -116,7 +116,7 @@ int sctl_cuda_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
 int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes, int* ctas_per_sm, int* n_launches, double* wave_eff);
 
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
- *   "const_min_targets" (default 2^19): at or above, sources are streamed through the constant bank in chunks
+ *   "const_min_targets" (default 2^18): at or above, sources are streamed through the constant bank in chunks
  *                       (FP64 only unless "const_fp32" is set to 1);
  *   "wide_min_targets"  (default 2^16): at or above (FP64), 4 targets per thread, one CTA per SM;
  *   "few_max_targets"   (default 2048): at or below, the warps of a CTA share 32 targets and split the sources.

@@ -89,7 +89,7 @@ struct Options {
   //   Nt <= few_max_targets   : shared-memory ring, all warps of a CTA share 32 targets and split the sources
   //   Nt >= wide_min_targets  : shared-memory ring, 4 targets per thread, one CTA per SM
   //   otherwise               : shared-memory ring, 2 targets per thread, two CTAs per SM
-  int64_t const_min_targets = 1 << 19;
+  int64_t const_min_targets = 1 << 18;
   int64_t few_max_targets = 2048;
   int64_t wide_min_targets = 1 << 16;
   int64_t const_fp32 = 0;  // FP32 gains nothing from the constant-bank path (rates in profiles/): off by default

@@ -72,7 +72,7 @@ def test_config4_kernels_fp32_fp64_large(sb, cpu_oracle, kernel):
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("kernel", list(cases.KERNELS))
 def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
-    """Large Nt (>= 2^19 by default; forced at 2^18 here) takes the chunk-streaming path (sources through the constant bank into uniform registers, one launch
+    """Large Nt (>= 2^18) takes the chunk-streaming path (sources through the constant bank into uniform registers, one launch
     per chunk, 2-CTA clusters at this size): several chunks, ragged last chunk, pre-filled v_trg, every kernel."""
     import torch
     from sctl_b200 import synth
@@ -100,7 +100,7 @@ def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
     torch.cuda.synchronize()
     assert torch.equal(d_v, d_w)
     sb.set_option("const_fp32", 0)
-    sb.set_option("const_min_targets", 1 << 19)
+    sb.set_option("const_min_targets", 1 << 18)
 
 
 def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
@@ -134,7 +134,7 @@ def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
         idx = np.arange(100) * (Nt // 100)
         want = cpu_oracle.eval("Stokes3D_FxU", r_src, None, v_src, r_trg.reshape(-1, 3)[idx].reshape(-1))
         assert rel_err(v.reshape(-1, 3)[idx].reshape(-1), want) <= 1e-12
-    sb.set_option("const_min_targets", 1 << 19)
+    sb.set_option("const_min_targets", 1 << 18)
 
 
 def test_target_permutation_equivariance(sb):

@@ -243,7 +243,7 @@ def test_every_eval_path_agrees(sb, cpu_oracle, kernel, dtype):
             got = K.Eval(None, r_trg, r_src, n_src, v_src, dtype=dtype)
             assert rel_err(got, want) <= TOL[dtype], (name, kernel, rel_err(got, want), sb.last_plan())
     finally:
-        for k, v in dict(few_max_targets=2048, wide_min_targets=1 << 16, const_min_targets=1 << 19, const_fp32=0).items():
+        for k, v in dict(few_max_targets=2048, wide_min_targets=1 << 16, const_min_targets=1 << 18, const_fp32=0).items():
             sb.set_option(k, v)
 
 
