@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 METRIC = "fp64_pair_interactions_per_s"
 UNIT = "pairs/s"
 F_ALG = {"Laplace3D_FxU": 11, "Laplace3D_DxU": 19, "Laplace3D_FxdU": 18, "Stokes3D_FxU": 29, "Stokes3D_DxU": 30}
+SCTL_FLOPS = {"Laplace3D_FxU": 6, "Laplace3D_DxU": 14, "Laplace3D_FxdU": 11, "Stokes3D_FxU": 23, "Stokes3D_DxU": 26}  # uKernel::FLOPS()
+FP_INSTR = {"Laplace3D_FxU": 12, "Laplace3D_DxU": 17, "Laplace3D_FxdU": 17, "Stokes3D_FxU": 22, "Stokes3D_DxU": 25}  # FP-pipe instructions per pair (f64)
 DIMS = {"Laplace3D_FxU": (1, 1, 0), "Laplace3D_DxU": (1, 1, 3), "Laplace3D_FxdU": (1, 3, 0), "Stokes3D_FxU": (3, 3, 0), "Stokes3D_DxU": (3, 3, 3)}
 
 
@@ -75,21 +77,21 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_arm(kernel, N, nsub, steps, warmup, want_result=False):
+def cpu_arm(kernel, N, nsub, steps, warmup, want_result=False, dtype=np.float64):
     """The reference's CPU Eval on all N sources x nsub strided targets; returns (pairs/s, info, subset result)."""
     import oracle
     from sctl_b200 import synth
     orc = oracle.best_cpu_oracle()
     k0, k1, nd = DIMS[kernel]
-    r_src, n_src, v_src, r_trg = synth.cube(N, N, k0, nd)
+    r_src, n_src, v_src, r_trg = synth.cube(N, N, k0, nd, dtype=dtype)
     idx = np.arange(nsub) * (N // nsub)
     sub = np.ascontiguousarray(r_trg.reshape(-1, 3)[idx]).reshape(-1)
     for _ in range(max(warmup, 2)):  # the reference's first calls pay OpenMP start-up and its scratch-pool first touch
-        orc.eval(kernel, r_src, n_src, v_src, sub)
+        orc.eval(kernel, r_src, n_src, v_src, sub, dtype=dtype)
     times, res = [], None
     for _ in range(steps):
         t0 = time.perf_counter()
-        res = orc.eval(kernel, r_src, n_src, v_src, sub)
+        res = orc.eval(kernel, r_src, n_src, v_src, sub, dtype=dtype)
         times.append(time.perf_counter() - t0)
     pairs = float(N) * nsub
     info = {"kind": orc.kind, "cores": orc.threads(), "sample": "all %d sources x %d strided targets (%.3g pairs) per step" % (N, nsub, pairs),
@@ -106,6 +108,7 @@ def main():
     ap.add_argument("--kernel", default="Stokes3D_FxU", choices=list(DIMS))
     ap.add_argument("--log2n", type=int, default=20, help="Ns = Nt = 2^log2n (BASELINE: 20)")
     ap.add_argument("--digits", type=int, default=-1)
+    ap.add_argument("--real", default="f64", choices=["f64", "f32"], help="arithmetic type (BASELINE metric: f64; configs[3] also names f32)")
     ap.add_argument("--cpu-targets", type=int, default=1 << 14, help="strided target subsample for the CPU baseline / parity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -117,8 +120,11 @@ def main():
     N = 1 << args.log2n
     kernel = args.kernel
     k0, k1, nd = DIMS[kernel]
-    workload = "%s GenericKernel::Eval FP64, Ns=Nt=2^%d uniform in unit cube (BASELINE configs[2])" % (kernel, args.log2n)
-    config = {"workload": workload, "kernel": kernel, "Ns": N, "Nt": N, "digits": args.digits, "inputs": "SplitMix64 streams (SURVEY 8d), f64",
+    npdt = np.float64 if args.real == "f64" else np.float32
+    rb = 8 if args.real == "f64" else 4
+    workload = "%s GenericKernel::Eval %s, Ns=Nt=2^%d uniform in unit cube%s" % (kernel, "FP64" if rb == 8 else "FP32", args.log2n,
+                                                                                 " (BASELINE configs[2])" if (kernel, args.log2n, rb) == ("Stokes3D_FxU", 20, 8) else "")
+    config = {"workload": workload, "kernel": kernel, "Ns": N, "Nt": N, "digits": args.digits, "inputs": "SplitMix64 streams (SURVEY 8d), generated in f64%s" % ("" if rb == 8 else ", cast to f32"),
               "sharding": "targets by contiguous block over %d GPU(s), sources replicated by NCCL broadcast" % args.gpus,
               "l2": "a 256 MiB buffer is overwritten between timed steps (L2 flush)"}
 
@@ -126,10 +132,10 @@ def main():
         if rank != 0:
             return
         nsub = min(N, 1 << 13)
-        val, info, _, sec = cpu_arm(kernel, N, nsub, args.steps, args.warmup)
+        val, info, _, sec = cpu_arm(kernel, N, nsub, args.steps, args.warmup, dtype=npdt)
         info["value"] = val
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
                 "config": config, "cpu_baseline": info, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "note": "reference CPU arm: SCTL's own OpenMP/Vec<> Eval on the host cores, bounded target sample per step"}
         print(json.dumps(line))
@@ -156,16 +162,17 @@ def main():
     # ---- inputs: every rank generates only its own slices (counter-based generator) ----------------------
     s0, s1 = block_range(N, rank, world)
     t0, t1 = block_range(N, rank, world)
-    r_src, n_src, v_src, r_trg = synth.cube(s1 - s0, t1 - t0, k0, nd, first_src=s0, first_trg=t0)
+    r_src, n_src, v_src, r_trg = synth.cube(s1 - s0, t1 - t0, k0, nd, dtype=npdt, first_src=s0, first_trg=t0)
+    tdt = torch.float64 if rb == 8 else torch.float32
     pin = lambda a: None if a is None else torch.from_numpy(a).pin_memory()
     h_r_src, h_n_src, h_v_src, h_r_trg = pin(r_src), pin(n_src), pin(v_src), pin(r_trg)
-    h_v_trg = torch.zeros((t1 - t0) * k1, dtype=torch.float64).pin_memory()
+    h_v_trg = torch.zeros((t1 - t0) * k1, dtype=tdt).pin_memory()
     to_dev = lambda h: None if h is None else h.to(dev, non_blocking=True)
     d_r_src, d_n_src, d_v_src, d_r_trg = to_dev(h_r_src), to_dev(h_n_src), to_dev(h_v_src), to_dev(h_r_trg)
-    d_v_trg = torch.zeros((t1 - t0) * k1, dtype=torch.float64, device=dev)
-    sh = ShardedEval(kernel, N, N, dtype=torch.float64, device=dev)
+    d_v_trg = torch.zeros((t1 - t0) * k1, dtype=tdt, device=dev)
+    sh = ShardedEval(kernel, N, N, dtype=tdt, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    h_out = torch.empty((t1 - t0) * k1, dtype=torch.float64).pin_memory()
+    h_out = torch.empty((t1 - t0) * k1, dtype=tdt).pin_memory()
     stream = torch.cuda.current_stream()
 
     def barrier():
@@ -203,7 +210,7 @@ def main():
         return per_step
 
     # ---- peak (roofline denominator) and warm-up -----------------------------------------------------------
-    peak_burst = sb.fma_peak(8, 50.0)
+    peak_burst = sb.fma_peak(rb, 50.0)
     for _ in range(args.warmup):
         step_resident()
     barrier()
@@ -229,14 +236,14 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         ker_ms.append(e0.elapsed_time(e1))
-    peak_sustained = sb.fma_peak(8, 1500.0)  # right after the timed region: same thermal / power state
+    peak_sustained = sb.fma_peak(rb, 1500.0)  # right after the timed region: same thermal / power state
 
     e2e = None
     if not args.no_e2e:
         step_e2e()
         e2e_ms = timed(step_e2e, args.steps)
-        bi = sum(h.numel() * 8 for h in (h_r_src, h_n_src, h_v_src, h_r_trg, h_v_trg) if h is not None)
-        e2e = {"value": float(N) * N * args.steps / (sum(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi * world, "d2h_bytes_per_step": h_out.numel() * 8 * world,
+        bi = sum(h.numel() * rb for h in (h_r_src, h_n_src, h_v_src, h_r_trg, h_v_trg) if h is not None)
+        e2e = {"value": float(N) * N * args.steps / (sum(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi * world, "d2h_bytes_per_step": h_out.numel() * rb * world,
                "ms_per_step": sum(e2e_ms) / args.steps, "api": "sctl_b200.sharded.ShardedEval.eval on pinned host buffers (H2D + replicate + Eval + D2H per step)"}
 
     if rank != 0:
@@ -251,25 +258,32 @@ def main():
     my_pairs = float(N) * (t1 - t0)
     k_ms = float(np.mean(ker_ms))
     achieved = my_pairs * F_ALG[kernel] / (k_ms * 1e-3) * 1e-12
-    roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": None,
-                "peak_source": "DFMA micro-benchmark in this run (sctl_cuda_fma_peak, 1.5 s sustained, FMA = 2 flop); burst 50 ms figure %.2f; MEASURED_PEAKS.json has no FP64 entry" % peak_burst,
-                "kernel": "eval_pairs_kernel<double, %s>" % kernel, "kernel_ms": k_ms, "pairs_per_launch": my_pairs, "flop_per_pair": F_ALG[kernel],
-                "frac_sctl_flops_convention": my_pairs * {"Stokes3D_FxU": 23, "Stokes3D_DxU": 26, "Laplace3D_FxU": 6, "Laplace3D_DxU": 14, "Laplace3D_FxdU": 11}[kernel] / (k_ms * 1e-3) * 1e-12 / peak_sustained,
-                "fp64_instr_per_pair": 22, "pipe_ceiling_frac": F_ALG[kernel] / (2.0 * 22) if kernel == "Stokes3D_FxU" else None}
+    # DRAM bytes of one pair-kernel launch from the ncu --set full capture of this same workload (profiles/r1_ncu_eval_const_*):
+    # 50.4 MB read + 0.02 MB written per constant-bank launch at 2^20 targets; null for any other workload
+    traffic = 50.43e6 if (kernel, args.log2n, rb, world) == ("Stokes3D_FxU", 20, 8, 1) else None
+    roofline = {"bound": "fp64" if rb == 8 else "fp32", "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": traffic,
+                "peak_source": "%s micro-benchmark in this run (sctl_cuda_fma_peak, 1.5 s sustained, FMA = 2 flop); burst 50 ms figure %.2f; MEASURED_PEAKS.json has no FP64/FP32 CUDA-core entry" % ("DFMA" if rb == 8 else "FFMA", peak_burst),
+                "note": "compute-bound on the FP64 CUDA-core pipe (pointwise rsqrt/FMA, ~0 bytes per pair): neither 'hbm' nor 'tensor' applies",
+                "kernel": "eval_pairs%s_kernel<%s, %s>" % ("_const" if plan["threads"] == 256 and plan["n_launches"] > 10 else "", "double" if rb == 8 else "float", kernel),
+                "kernel_ms_per_step": k_ms, "pair_kernel_launches_per_step": max(1, plan["n_launches"] - 3) if plan["n_launches"] > 10 else 1,
+                "pairs_per_step": my_pairs, "flop_per_pair": F_ALG[kernel],
+                "frac_sctl_flops_convention": my_pairs * SCTL_FLOPS[kernel] / (k_ms * 1e-3) * 1e-12 / peak_sustained,
+                "fp_instr_per_pair": FP_INSTR[kernel], "pipe_ceiling_frac": F_ALG[kernel] / (2.0 * FP_INSTR[kernel])}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(res_ms) / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.real, "data": "synthetic", "config": config, "clocks": clocks,
             "gpu_launches": int(plan["n_launches"]) * args.steps, "launch_plan": plan, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
 
     if not args.no_cpu_baseline and world == 1:
         nsub = min(N, args.cpu_targets)
-        val, info, (idx, cpu_res), _ = cpu_arm(kernel, N, nsub, 2, 2, want_result=True)
+        val, info, (idx, cpu_res), _ = cpu_arm(kernel, N, nsub, 2, 2, want_result=True, dtype=npdt)
         info.update({"value": val, "unit": UNIT})
         line["cpu_baseline"] = info
         got = full.cpu().numpy().reshape(-1, k1)[idx].reshape(-1)
-        line["parity"] = {"max_abs_err_over_vinf": float(np.abs(got - cpu_res).max() / np.abs(full.cpu().numpy()).max()), "gate": 1e-12,
+        line["parity"] = {"max_abs_err_over_vinf": float(np.abs(got.astype(np.float64) - cpu_res.astype(np.float64)).max() / np.abs(full.cpu().numpy()).max()),
+                          "gate": 1e-12 if rb == 8 else "1e-5 for Ns <= 2^14; beyond that two FP32 summation orders differ by more (SURVEY 7.3)",
                           "checked": "%d strided targets x all sources vs the CPU arm above" % nsub}
     print(json.dumps(line))
     if world > 1:

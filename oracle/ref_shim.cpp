@@ -175,6 +175,18 @@ int sctl_ref_dims(int kernel_id, int* k0, int* k1, int* nd, int* flops, double* 
   }
 }
 
+// Vector<double>::Write / Matrix<double>::Write (vector.txx:132-144, matrix.txx) -- fixtures for sctl_b200/io.py
+int sctl_ref_vector_write(const char* path, int64_t n, const double* x) {
+  sctl::Vector<double> v(n, (sctl::Iterator<double>)(double*)x, false);
+  v.Write(path);
+  return 0;
+}
+int sctl_ref_matrix_write(const char* path, int64_t rows, int64_t cols, const double* x) {
+  sctl::Matrix<double> m(rows, cols, (sctl::Iterator<double>)(double*)x, false);
+  m.Write(path);
+  return 0;
+}
+
 int sctl_ref_threads() { return omp_get_max_threads(); }
 int sctl_ref_veclen(int real_bytes) { return real_bytes == 8 ? sctl::DefaultVecLen<double>() : sctl::DefaultVecLen<float>(); }
 

@@ -35,6 +35,15 @@ def main():
         out["rsqrt/f64/%d" % digits] = ref.rsqrt(x, digits)
     for digits in (-1, 4, 7):
         out["rsqrt/f32/%d" % digits] = ref.rsqrt(x.astype(np.float32), digits)
+    # SCTL binary container fixtures written by the reference's own Vector::Write / Matrix::Write
+    import ctypes
+    here = os.path.dirname(os.path.abspath(__file__))
+    vec = np.array([1.5, -2.25, 3.0, 0.0, 1e-300, -7.0, 42.0])
+    mat = np.arange(6, dtype=np.float64).reshape(2, 3) - 2.5
+    ref.lib.sctl_ref_vector_write.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p]
+    ref.lib.sctl_ref_matrix_write.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]
+    ref.lib.sctl_ref_vector_write(os.path.join(here, "sctl_vector_f64.bin").encode(), vec.size, vec.ctypes.data_as(ctypes.c_void_p))
+    ref.lib.sctl_ref_matrix_write(os.path.join(here, "sctl_matrix_f64.bin").encode(), 2, 3, mat.ctypes.data_as(ctypes.c_void_p))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_eval.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "%d arrays, %.1f KB" % (len(out), os.path.getsize(path) / 1024))
