@@ -30,7 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "fp64_pair_interactions_per_s"
+METRIC = "fp64_pair_interactions_per_s"  # BASELINE.json metric; "fp32_..." when run with --real f32
 UNIT = "pairs/s"
 F_ALG = {"Laplace3D_FxU": 11, "Laplace3D_DxU": 19, "Laplace3D_FxdU": 18, "Stokes3D_FxU": 29, "Stokes3D_DxU": 30}
 SCTL_FLOPS = {"Laplace3D_FxU": 6, "Laplace3D_DxU": 14, "Laplace3D_FxdU": 11, "Stokes3D_FxU": 23, "Stokes3D_DxU": 26}  # uKernel::FLOPS()
@@ -120,6 +120,8 @@ def main():
     N = 1 << args.log2n
     kernel = args.kernel
     k0, k1, nd = DIMS[kernel]
+    global METRIC
+    METRIC = "fp64_pair_interactions_per_s" if args.real == "f64" else "fp32_pair_interactions_per_s"
     npdt = np.float64 if args.real == "f64" else np.float32
     rb = 8 if args.real == "f64" else 4
     workload = "%s GenericKernel::Eval %s, Ns=Nt=2^%d uniform in unit cube%s" % (kernel, "FP64" if rb == 8 else "FP32", args.log2n,
@@ -185,7 +187,18 @@ def main():
         v = sh.eval(d_r_src, d_n_src, d_v_src, d_r_trg, v_trg_local=d_v_trg, digits=args.digits)
         return sh.gather(v) if world > 1 else v
 
+    K = sb.KERNELS[kernel]
+    np_view = lambda h: None if h is None else h.numpy()
+
+    def step_e2e_cabi():
+        # N = 1: the reference-facing entry itself -- sctl_cuda_eval on HOST buffers (H2D of every input, pack, probe, pair
+        # kernels, D2H of the result, all inside the call); the caller's v_trg is zero here, Eval accumulates into it
+        h_v_trg.zero_()
+        return K.Eval(np_view(h_v_trg), np_view(h_r_trg), np_view(h_r_src), np_view(h_n_src), np_view(h_v_src), digits=args.digits, dtype=npdt)
+
     def step_e2e():
+        if world == 1:
+            return step_e2e_cabi()
         a, b, c, d = to_dev(h_r_src), to_dev(h_n_src), to_dev(h_v_src), to_dev(h_r_trg)
         v = to_dev(h_v_trg)  # Eval accumulates: the caller's v_trg goes up with the inputs
         v = sh.eval(a, b, c, d, v_trg_local=v, digits=args.digits)
@@ -244,7 +257,8 @@ def main():
         e2e_ms = timed(step_e2e, args.steps)
         bi = sum(h.numel() * rb for h in (h_r_src, h_n_src, h_v_src, h_r_trg, h_v_trg) if h is not None)
         e2e = {"value": float(N) * N * args.steps / (sum(e2e_ms) * 1e-3), "unit": UNIT, "h2d_bytes_per_step": bi * world, "d2h_bytes_per_step": h_out.numel() * rb * world,
-               "ms_per_step": sum(e2e_ms) / args.steps, "api": "sctl_b200.sharded.ShardedEval.eval on pinned host buffers (H2D + replicate + Eval + D2H per step)"}
+               "ms_per_step": sum(e2e_ms) / args.steps, "api": ("sctl_cuda_eval (C ABI, host pointers: H2D + pack + probe + pair kernels + D2H inside the call)" if world == 1 else
+                       "sctl_b200.sharded.ShardedEval.eval on pinned host buffers (H2D of each rank's slices + NCCL replicate + Eval + D2H per step)")}
 
     if rank != 0:
         if world > 1:
