@@ -57,7 +57,12 @@ enum sctl_cuda_kernel_id {
   SCTL_CUDA_LAPLACE3D_DXDU = 9,     /* sctl::Laplace3D_DxdU    kernel_functions.hpp:391-412  (1,3,3) */
   SCTL_CUDA_BIOTSAVART3D_FXU = 10,  /* sctl::BiotSavart3D_FxU  kernel_functions.hpp:414-448  (3,3,0) */
   SCTL_CUDA_BIOTSAVART3D_FXDU = 11, /* sctl::BiotSavart3D_FxdU kernel_functions.hpp:450-483  (3,9,0) */
-  SCTL_CUDA_NUM_KERNELS = 12
+  /* Helmholtz: complex values as adjacent (re, im) pairs; ctx = HOST pointer to the wavenumber, one Real */
+  SCTL_CUDA_HELMHOLTZ3D_FXU = 12,      /* sctl::Helmholtz3D_FxU      kernel_functions.hpp:490-533  (2,2,0) */
+  SCTL_CUDA_HELMHOLTZ3D_DXU = 13,      /* sctl::Helmholtz3D_DxU      kernel_functions.hpp:535-578  (2,2,3) */
+  SCTL_CUDA_HELMHOLTZ3D_FXDU = 14,     /* sctl::Helmholtz3D_FxdU     kernel_functions.hpp:580-627  (2,6,0) */
+  SCTL_CUDA_HELMHOLTZDIFF3D_FXDU = 15, /* sctl::HelmholtzDiff3D_FxdU kernel_functions.hpp:629-659  (2,6,0) */
+  SCTL_CUDA_NUM_KERNELS = 16
 };
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
@@ -87,10 +92,13 @@ int sctl_cuda_kernel_info(int kernel_id, int* k0, int* k1, int* nd, int* flops, 
 
 int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
                    const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg,
-                   const void* ctx, int64_t ctx_bytes /* uKernel context (GetCtxPtr); unused by the five kernels */);
+                   const void* ctx, int64_t ctx_bytes /* uKernel context (GetCtxPtr, generic-kernel.hpp:79): a HOST pointer; the
+                                                         Helmholtz kernels read one Real (the wavenumber) from it, the others
+                                                         ignore it; ctx_bytes = real_bytes or 0 */);
 
 int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
-                            const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM);
+                            const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM,
+                            const void* ctx, int64_t ctx_bytes);
 
 /* ---- the hot path: device pointers on the current device, enqueued on `stream` -------------- */
 /* (cudaStream_t passed as void*; NULL = the legacy default stream.)  Asynchronous: returns after enqueueing.
@@ -98,11 +106,11 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
 
 int sctl_cuda_eval_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
                           const void* d_r_src, const void* d_n_src, const void* d_v_src, const void* d_r_trg, void* d_v_trg,
-                          void* stream);
+                          const void* ctx /* HOST pointer */, int64_t ctx_bytes, void* stream);
 
 int sctl_cuda_kernel_matrix_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
                                    const void* d_r_src, const void* d_n_src, const void* d_r_trg, void* d_M, int64_t ldM,
-                                   void* stream);
+                                   const void* ctx /* HOST pointer */, int64_t ctx_bytes, void* stream);
 
 /* ---- measurement and test hooks ------------------------------------------------------------- */
 

@@ -65,13 +65,14 @@ inline void eval_host(int kernel_id, Integer K0, Integer K1, Integer ND, Integer
   if (Ns == 0 || Nt == 0) return;
   const Real* xn = ND ? &n_src[0] : nullptr;
   if (sctl_cuda_eval(kernel_id, real_bytes<Real>::value, (int)(digits >= 16 ? -1 : digits), Ns, Nt, &r_src[0], xn, &v_src[0], &r_trg[0], &v_trg[0],
-                     ctx_ptr, 0))
+                     ctx_ptr, ctx_ptr ? (int64_t)sizeof(Real) : 0))
     die("sctl_cuda_eval");
 }
 
 // Body of GenericKernel<uKernel>::KernelMatrix<Real,omp,digits> (generic-kernel.txx:213-329).
 template <class Real, class Mat, class VecIn>
-inline void kernel_matrix_host(int kernel_id, Integer K0, Integer K1, Integer ND, Integer digits, Mat& M, const VecIn& Xt, const VecIn& Xs, const VecIn& Xn) {
+inline void kernel_matrix_host(int kernel_id, Integer K0, Integer K1, Integer ND, Integer digits, Mat& M, const VecIn& Xt, const VecIn& Xs, const VecIn& Xn,
+                               const void* ctx_ptr = nullptr) {
   constexpr Integer DIM = 3;
   const Long Ns = Xs.Dim() / DIM;
   const Long Nt = Xt.Dim() / DIM;
@@ -84,7 +85,8 @@ inline void kernel_matrix_host(int kernel_id, Integer K0, Integer K1, Integer ND
   }
   if (Ns == 0 || Nt == 0) return;
   const Real* xn = ND ? &Xn[0] : nullptr;
-  if (sctl_cuda_kernel_matrix(kernel_id, real_bytes<Real>::value, (int)(digits >= 16 ? -1 : digits), Ns, Nt, &Xs[0], xn, &Xt[0], &M[0][0], Nt * K1))
+  if (sctl_cuda_kernel_matrix(kernel_id, real_bytes<Real>::value, (int)(digits >= 16 ? -1 : digits), Ns, Nt, &Xs[0], xn, &Xt[0], &M[0][0], Nt * K1,
+                              ctx_ptr, ctx_ptr ? (int64_t)sizeof(Real) : 0))
     die("sctl_cuda_kernel_matrix");
 }
 
@@ -120,6 +122,11 @@ SCTL_CUDA_UKERNEL(Laplace3D_Fxd2U, SCTL_CUDA_LAPLACE3D_FXD2U, "Laplace3D-Fxd2U",
 SCTL_CUDA_UKERNEL(Laplace3D_DxdU, SCTL_CUDA_LAPLACE3D_DXDU, "Laplace3D-DxdU", 1, 3, 3, 22, 1, 4);     // :391-412
 SCTL_CUDA_UKERNEL(BiotSavart3D_FxU, SCTL_CUDA_BIOTSAVART3D_FXU, "BiotSavart3D-FxU", 3, 3, 0, 15, 1, 4);      // :414-448
 SCTL_CUDA_UKERNEL(BiotSavart3D_FxdU, SCTL_CUDA_BIOTSAVART3D_FXDU, "BiotSavart3D-FxdU", 3, 9, 0, 51, -1, 4);  // :450-483
+// Helmholtz: SetCtxPtr(&mu) with mu of the evaluation's Real type (kernel_functions.hpp:484-488)
+SCTL_CUDA_UKERNEL(Helmholtz3D_FxU, SCTL_CUDA_HELMHOLTZ3D_FXU, "Helmholtz3D-FxU", 2, 2, 0, 20, 1, 4);               // :490-533
+SCTL_CUDA_UKERNEL(Helmholtz3D_DxU, SCTL_CUDA_HELMHOLTZ3D_DXU, "Helmholtz3D-DxU", 2, 2, 3, 29, -1, 4);              // :535-578
+SCTL_CUDA_UKERNEL(Helmholtz3D_FxdU, SCTL_CUDA_HELMHOLTZ3D_FXDU, "Helmholtz3D-FxdU", 2, 6, 0, 35, 1, 4);            // :580-627
+SCTL_CUDA_UKERNEL(HelmholtzDiff3D_FxdU, SCTL_CUDA_HELMHOLTZDIFF3D_FXDU, "HelmholtzDiff3D-FxdU", 2, 6, 0, 41, 1, 4); // :629-659
 #undef SCTL_CUDA_UKERNEL
 
 }  // namespace kernel_impl
@@ -158,7 +165,7 @@ template <class uKernel> class GenericKernel : public uKernel {
   // M[(s*K0+k0)][(t*K1+k1)] = scale * K_{k0,k1}(x_t - x_s, n_s), overwriting   (generic-kernel.hpp:124).
   template <class Real, bool enable_openmp = false, Integer digits = -1, class Mat, class VecIn>
   void KernelMatrix(Mat& M, const VecIn& Xt, const VecIn& Xs, const VecIn& Xn) const {
-    detail::kernel_matrix_host<Real>(uKernel::kernel_id, KDIM0, KDIM1, N_DIM, digits, M, Xt, Xs, Xn);
+    detail::kernel_matrix_host<Real>(uKernel::kernel_id, KDIM0, KDIM1, N_DIM, digits, M, Xt, Xs, Xn, ctx_ptr);
   }
 
  private:
@@ -177,6 +184,10 @@ using Laplace3D_Fxd2U = GenericKernel<kernel_impl::Laplace3D_Fxd2U>;
 using Laplace3D_DxdU = GenericKernel<kernel_impl::Laplace3D_DxdU>;
 using BiotSavart3D_FxU = GenericKernel<kernel_impl::BiotSavart3D_FxU>;
 using BiotSavart3D_FxdU = GenericKernel<kernel_impl::BiotSavart3D_FxdU>;
+using Helmholtz3D_FxU = GenericKernel<kernel_impl::Helmholtz3D_FxU>;
+using Helmholtz3D_DxU = GenericKernel<kernel_impl::Helmholtz3D_DxU>;
+using Helmholtz3D_FxdU = GenericKernel<kernel_impl::Helmholtz3D_FxdU>;
+using HelmholtzDiff3D_FxdU = GenericKernel<kernel_impl::HelmholtzDiff3D_FxdU>;
 
 }  // namespace sctl_cuda
 

@@ -5,12 +5,12 @@
 //     sctl::GenericKernel<kernel_impl::X>::Eval<Real,omp,digits>         (generic-kernel.txx:102-211)
 //     sctl::GenericKernel<kernel_impl::X>::KernelMatrix<Real,omp,digits> (generic-kernel.txx:213-329)
 // for X in {Laplace3D_FxU, Laplace3D_DxU, Laplace3D_FxdU, Stokes3D_FxU, Stokes3D_DxU} (the north-star five) and
-// {Stokes3D_FxT, Stokes3D_FSxU, Stokes3D_FxUP, Laplace3D_Fxd2U, Laplace3D_DxdU, BiotSavart3D_FxU, BiotSavart3D_FxdU},
-// so every caller that
+// {Stokes3D_FxT, Stokes3D_FSxU, Stokes3D_FxUP, Laplace3D_Fxd2U, Laplace3D_DxdU, BiotSavart3D_FxU, BiotSavart3D_FxdU,
+//  Helmholtz3D_FxU, Helmholtz3D_DxU, Helmholtz3D_FxdU, HelmholtzDiff3D_FxdU} -- all sixteen kernels -- so every caller that
 // goes through those entry points -- user code, the runtime-digits trampoline Eval<Real,omp>(..., digits, self)
 // (generic-kernel.txx:72-100) that ParticleFMM stores (fmm-wrapper.txx:450-451), BoundaryIntegralOp's
 // KernelMatrix calls (boundary_integral.txx:1197,1211) -- runs on the B200 with unchanged source.  SCTL's headers
-// are not modified; the four Helmholtz kernels keep their CPU implementation; uKerMatrix/uKerApply stay available
+// are not modified; uKerMatrix/uKerApply stay available
 // to PVFMM-style callers.  Profile::IncrementCounter(FLOP, Ns*Nt*FLOPS()) is preserved (generic-kernel.txx:210,224).
 #ifndef SCTL_CUDA_SCTL_DROPIN_HPP_
 #define SCTL_CUDA_SCTL_DROPIN_HPP_
@@ -30,7 +30,7 @@ namespace sctl {
   }                                                                                                                                          \
   template <> template <class Real, bool enable_openmp, Integer digits>                                                                      \
   void GenericKernel<kernel_impl::UKER>::KernelMatrix(Matrix<Real>& M, const Vector<Real>& Xt, const Vector<Real>& Xs, const Vector<Real>& Xn) const { \
-    ::sctl_cuda::detail::kernel_matrix_host<Real>(ID, K0, K1, ND, digits, M, Xt, Xs, Xn);                                                    \
+    ::sctl_cuda::detail::kernel_matrix_host<Real>(ID, K0, K1, ND, digits, M, Xt, Xs, Xn, ctx_ptr);                                                    \
     Profile::IncrementCounter(ProfileCounter::FLOP, (Xs.Dim() / 3) * (Xt.Dim() / 3) * kernel_impl::UKER::FLOPS());                           \
   }
 
@@ -46,6 +46,10 @@ SCTL_CUDA_DROPIN(Laplace3D_Fxd2U, SCTL_CUDA_LAPLACE3D_FXD2U, 1, 9, 0)
 SCTL_CUDA_DROPIN(Laplace3D_DxdU, SCTL_CUDA_LAPLACE3D_DXDU, 1, 3, 3)
 SCTL_CUDA_DROPIN(BiotSavart3D_FxU, SCTL_CUDA_BIOTSAVART3D_FXU, 3, 3, 0)
 SCTL_CUDA_DROPIN(BiotSavart3D_FxdU, SCTL_CUDA_BIOTSAVART3D_FXDU, 3, 9, 0)
+SCTL_CUDA_DROPIN(Helmholtz3D_FxU, SCTL_CUDA_HELMHOLTZ3D_FXU, 2, 2, 0)
+SCTL_CUDA_DROPIN(Helmholtz3D_DxU, SCTL_CUDA_HELMHOLTZ3D_DXU, 2, 2, 3)
+SCTL_CUDA_DROPIN(Helmholtz3D_FxdU, SCTL_CUDA_HELMHOLTZ3D_FXDU, 2, 6, 0)
+SCTL_CUDA_DROPIN(HelmholtzDiff3D_FxdU, SCTL_CUDA_HELMHOLTZDIFF3D_FXDU, 2, 6, 0)
 #undef SCTL_CUDA_DROPIN
 
 }  // namespace sctl

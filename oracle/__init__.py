@@ -19,14 +19,25 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
 KERNEL_IDS = {"Laplace3D_FxU": 0, "Laplace3D_DxU": 1, "Laplace3D_FxdU": 2, "Stokes3D_FxU": 3, "Stokes3D_DxU": 4, "Stokes3D_FxT": 5, "Stokes3D_FSxU": 6,
-              "Stokes3D_FxUP": 7, "Laplace3D_Fxd2U": 8, "Laplace3D_DxdU": 9, "BiotSavart3D_FxU": 10, "BiotSavart3D_FxdU": 11}
+              "Stokes3D_FxUP": 7, "Laplace3D_Fxd2U": 8, "Laplace3D_DxdU": 9, "BiotSavart3D_FxU": 10, "BiotSavart3D_FxdU": 11,
+              "Helmholtz3D_FxU": 12, "Helmholtz3D_DxU": 13, "Helmholtz3D_FxdU": 14, "HelmholtzDiff3D_FxdU": 15}
 # (KDIM0, KDIM1, N_DIM): generic-kernel.hpp:22-41 applied to kernel_functions.hpp:43,72,92,136,191
 KERNEL_DIMS = {0: (1, 1, 0), 1: (1, 1, 3), 2: (1, 3, 0), 3: (3, 3, 0), 4: (3, 3, 3), 5: (3, 9, 0), 6: (4, 3, 0), 7: (3, 4, 0), 8: (1, 9, 0), 9: (1, 3, 3),
-               10: (3, 3, 0), 11: (3, 9, 0)}
+               10: (3, 3, 0), 11: (3, 9, 0), 12: (2, 2, 0), 13: (2, 2, 3), 14: (2, 6, 0), 15: (2, 6, 0)}
+
+
+# Wavenumber used by every Helmholtz fixture and test unless a call passes ctx explicitly (tests/golden/cases.py CTX)
+DEFAULT_HELMHOLTZ_CTX = 1.7
 
 
 def _kid(kernel):
     return KERNEL_IDS[kernel] if isinstance(kernel, str) else int(kernel)
+
+
+def _ctx(kid, ctx):
+    if ctx is None:
+        return DEFAULT_HELMHOLTZ_CTX if kid >= 12 else 0.0
+    return float(ctx)
 
 
 def build(verbose=False):
@@ -82,8 +93,8 @@ class PortOracle(_Base):
             build()
         self.lib = C.CDLL(path)
         L = self.lib
-        L.oracle_eval.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 5
-        L.oracle_kernel_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 4 + [C.c_int64]
+        L.oracle_eval.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 5 + [C.c_double]
+        L.oracle_kernel_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 4 + [C.c_int64, C.c_double]
         L.oracle_rsqrt_newton.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.oracle_newton_iters.argtypes = [C.c_int, C.c_int]
         L.oracle_splitmix_fill.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_double, C.c_void_p]
@@ -92,18 +103,18 @@ class PortOracle(_Base):
     def threads(self):
         return int(self.lib.oracle_threads())
 
-    def eval(self, kernel, r_src, n_src, v_src, r_trg, v_trg=None, dtype=np.float64, omp=True, digits=-1):
+    def eval(self, kernel, r_src, n_src, v_src, r_trg, v_trg=None, dtype=np.float64, omp=True, digits=-1, ctx=None):
         kid, k0, k1, nd, ns, nt, r_src, n_src, v_src, r_trg = self._prep(kernel, r_src, n_src, v_src, r_trg, dtype)
         out = np.zeros(nt * k1, dtype=dtype) if v_trg is None else np.ascontiguousarray(v_trg, dtype=dtype).reshape(-1).copy()
         assert out.size == nt * k1
-        rc = self.lib.oracle_eval(kid, out.itemsize, int(omp), ns, nt, self._p(r_src), self._p(n_src), self._p(v_src), self._p(r_trg), self._p(out))
+        rc = self.lib.oracle_eval(kid, out.itemsize, int(omp), ns, nt, self._p(r_src), self._p(n_src), self._p(v_src), self._p(r_trg), self._p(out), _ctx(kid, ctx))
         assert rc == 0, rc
         return out
 
-    def kernel_matrix(self, kernel, r_src, n_src, r_trg, dtype=np.float64, omp=True, digits=-1):
+    def kernel_matrix(self, kernel, r_src, n_src, r_trg, dtype=np.float64, omp=True, digits=-1, ctx=None):
         kid, k0, k1, nd, ns, nt, r_src, n_src, _, r_trg = self._prep(kernel, r_src, n_src, None, r_trg, dtype)
         M = np.full((ns * k0, nt * k1), np.nan, dtype=dtype)
-        rc = self.lib.oracle_kernel_matrix(kid, M.itemsize, int(omp), ns, nt, self._p(r_src), self._p(n_src), self._p(r_trg), self._p(M), nt * k1)
+        rc = self.lib.oracle_kernel_matrix(kid, M.itemsize, int(omp), ns, nt, self._p(r_src), self._p(n_src), self._p(r_trg), self._p(M), nt * k1, _ctx(kid, ctx))
         assert rc == 0, rc
         return M
 
@@ -148,8 +159,8 @@ class RefOracle(_Base):
         self.isa = isa
         self.lib = C.CDLL(path)
         L = self.lib
-        L.sctl_ref_eval.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 5
-        L.sctl_ref_kernel_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 4
+        L.sctl_ref_eval.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 6
+        L.sctl_ref_kernel_matrix.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64] + [C.c_void_p] * 5
         L.sctl_ref_rsqrt.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.sctl_ref_dims.argtypes = [C.c_int] + [C.c_void_p] * 7 + [C.c_int]
         L.sctl_ref_veclen.argtypes = [C.c_int]
@@ -160,21 +171,23 @@ class RefOracle(_Base):
     def veclen(self, real_bytes):
         return int(self.lib.sctl_ref_veclen(real_bytes))
 
-    def eval(self, kernel, r_src, n_src, v_src, r_trg, v_trg=None, dtype=np.float64, omp=True, digits=-1):
+    def eval(self, kernel, r_src, n_src, v_src, r_trg, v_trg=None, dtype=np.float64, omp=True, digits=-1, ctx=None):
         kid, k0, k1, nd, ns, nt, r_src, n_src, v_src, r_trg = self._prep(kernel, r_src, n_src, v_src, r_trg, dtype)
         out = np.zeros(nt * k1, dtype=dtype) if v_trg is None else np.ascontiguousarray(v_trg, dtype=dtype).reshape(-1).copy()
         assert out.size == nt * k1
         if nt == 0 or out.size == 0:
             return out
-        rc = self.lib.sctl_ref_eval(kid, out.itemsize, int(omp), digits, ns, nt, self._p(r_src), self._p(n_src), self._p(v_src), self._p(r_trg), self._p(out))
+        mu = np.array([_ctx(kid, ctx)], dtype=dtype)  # the context is a pointer to one Real of the evaluation type
+        rc = self.lib.sctl_ref_eval(kid, out.itemsize, int(omp), digits, ns, nt, self._p(r_src), self._p(n_src), self._p(v_src), self._p(r_trg), self._p(out), self._p(mu))
         assert rc == 0, rc
         return out
 
-    def kernel_matrix(self, kernel, r_src, n_src, r_trg, dtype=np.float64, omp=True, digits=-1):
+    def kernel_matrix(self, kernel, r_src, n_src, r_trg, dtype=np.float64, omp=True, digits=-1, ctx=None):
         kid, k0, k1, nd, ns, nt, r_src, n_src, _, r_trg = self._prep(kernel, r_src, n_src, None, r_trg, dtype)
         M = np.full((ns * k0, nt * k1), np.nan, dtype=dtype)
         if M.size:
-            rc = self.lib.sctl_ref_kernel_matrix(kid, M.itemsize, int(omp), digits, ns, nt, self._p(r_src), self._p(n_src), self._p(r_trg), self._p(M))
+            mu = np.array([_ctx(kid, ctx)], dtype=dtype)
+            rc = self.lib.sctl_ref_kernel_matrix(kid, M.itemsize, int(omp), digits, ns, nt, self._p(r_src), self._p(n_src), self._p(r_trg), self._p(M), self._p(mu))
             assert rc == 0, rc
         return M
 

@@ -19,9 +19,10 @@
 namespace {
 
 template <class Real, class Ker, bool omp, sctl::Integer digits>
-void eval_t(int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg) {
+void eval_t(int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, const void* ctx) {
   using namespace sctl;
   Ker ker;
+  ker.SetCtxPtr((void*)ctx);  // Helmholtz: pointer to the wavenumber, of type Real (kernel_functions.hpp:484-488)
   constexpr Integer K0 = Ker::SrcDim(), K1 = Ker::TrgDim(), ND = Ker::NormalDim();
   const Vector<Real> Xs(Ns * 3, (Iterator<Real>)(Real*)r_src, false);
   const Vector<Real> Xn(n_src ? Ns * ND : 0, (Iterator<Real>)(Real*)n_src, false);
@@ -32,9 +33,10 @@ void eval_t(int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const 
 }
 
 template <class Real, class Ker, bool omp, sctl::Integer digits>
-void kmat_t(int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M) {
+void kmat_t(int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, const void* ctx) {
   using namespace sctl;
   Ker ker;
+  ker.SetCtxPtr((void*)ctx);
   constexpr Integer K0 = Ker::SrcDim(), K1 = Ker::TrgDim(), ND = Ker::NormalDim();
   const Vector<Real> Xs(Ns * 3, (Iterator<Real>)(Real*)r_src, false);
   const Vector<Real> Xn(n_src ? Ns * ND : 0, (Iterator<Real>)(Real*)n_src, false);
@@ -71,6 +73,10 @@ template <class Real, class... A> int eval_ker(int kernel_id, int omp, int digit
     case 9: return eval_omp<Real, sctl::Laplace3D_DxdU>(omp, digits, a...);
     case 10: return eval_omp<Real, sctl::BiotSavart3D_FxU>(omp, digits, a...);
     case 11: return eval_omp<Real, sctl::BiotSavart3D_FxdU>(omp, digits, a...);
+    case 12: return eval_omp<Real, sctl::Helmholtz3D_FxU>(omp, digits, a...);
+    case 13: return eval_omp<Real, sctl::Helmholtz3D_DxU>(omp, digits, a...);
+    case 14: return eval_omp<Real, sctl::Helmholtz3D_FxdU>(omp, digits, a...);
+    case 15: return eval_omp<Real, sctl::HelmholtzDiff3D_FxdU>(omp, digits, a...);
     default: return 1;
   }
 }
@@ -94,6 +100,10 @@ template <class Real, class... A> int kmat_ker(int kernel_id, int omp, int digit
     case 9: return kmat_omp<Real, sctl::Laplace3D_DxdU>(omp, digits, a...);
     case 10: return kmat_omp<Real, sctl::BiotSavart3D_FxU>(omp, digits, a...);
     case 11: return kmat_omp<Real, sctl::BiotSavart3D_FxdU>(omp, digits, a...);
+    case 12: return kmat_omp<Real, sctl::Helmholtz3D_FxU>(omp, digits, a...);
+    case 13: return kmat_omp<Real, sctl::Helmholtz3D_DxU>(omp, digits, a...);
+    case 14: return kmat_omp<Real, sctl::Helmholtz3D_FxdU>(omp, digits, a...);
+    case 15: return kmat_omp<Real, sctl::HelmholtzDiff3D_FxdU>(omp, digits, a...);
     default: return 1;
   }
 }
@@ -117,16 +127,16 @@ template <class Real, sctl::Integer digits> void rsqrt_t(int64_t n, const Real* 
 extern "C" {
 
 // v_trg[Nt*K1] += scale * sum_s K(x_t - x_s, n_s) f_s   via the reference's own Eval.
-int sctl_ref_eval(int kernel_id, int real_bytes, int omp, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg) {
-  if (real_bytes == 8) return eval_ker<double>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg);
-  if (real_bytes == 4) return eval_ker<float>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg);
+int sctl_ref_eval(int kernel_id, int real_bytes, int omp, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, const void* ctx) {
+  if (real_bytes == 8) return eval_ker<double>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx);
+  if (real_bytes == 4) return eval_ker<float>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx);
   return 3;
 }
 
 // M[(Ns*K0) x (Nt*K1)] row-major, overwritten, via the reference's own KernelMatrix.
-int sctl_ref_kernel_matrix(int kernel_id, int real_bytes, int omp, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M) {
-  if (real_bytes == 8) return kmat_ker<double>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, r_trg, M);
-  if (real_bytes == 4) return kmat_ker<float>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, r_trg, M);
+int sctl_ref_kernel_matrix(int kernel_id, int real_bytes, int omp, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, const void* ctx) {
+  if (real_bytes == 8) return kmat_ker<double>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, r_trg, M, ctx);
+  if (real_bytes == 4) return kmat_ker<float>(kernel_id, omp, digits, Ns, Nt, r_src, n_src, r_trg, M, ctx);
   return 3;
 }
 
@@ -171,6 +181,10 @@ int sctl_ref_dims(int kernel_id, int* k0, int* k1, int* nd, int* flops, double* 
     case 9: fill(sctl::Laplace3D_DxdU()); return 0;
     case 10: fill(sctl::BiotSavart3D_FxU()); return 0;
     case 11: fill(sctl::BiotSavart3D_FxdU()); return 0;
+    case 12: fill(sctl::Helmholtz3D_FxU()); return 0;
+    case 13: fill(sctl::Helmholtz3D_DxU()); return 0;
+    case 14: fill(sctl::Helmholtz3D_FxdU()); return 0;
+    case 15: fill(sctl::HelmholtzDiff3D_FxdU()); return 0;
     default: return 1;
   }
 }

@@ -22,12 +22,14 @@
 #endif
 
 /* (KDIM0, KDIM1, N_DIM) deduced by generic-kernel.hpp:22-41 from each uKerMatrix signature. */
-#define NKER 12
-static const int KDIMS[NKER][3] = {{1,1,0}, {1,1,3}, {1,3,0}, {3,3,0}, {3,3,3}, {3,9,0}, {4,3,0}, {3,4,0}, {1,9,0}, {1,3,3}, {3,3,0}, {3,9,0}};
+#define NKER 16
+static const int KDIMS[NKER][3] = {{1,1,0}, {1,1,3}, {1,3,0}, {3,3,0}, {3,3,3}, {3,9,0}, {4,3,0}, {3,4,0}, {1,9,0}, {1,3,3}, {3,3,0}, {3,9,0},
+                                    {2,2,0}, {2,2,3}, {2,6,0}, {2,6,0}};
 /* uKernel::FLOPS(): kernel_functions.hpp:37-39, 66-68, 86-88, 130-132, 185-187. */
-static const int KFLOPS[NKER] = {6, 14, 11, 23, 26, 39, 26, 26, 25, 22, 15, 51};  /* + :225-227, 261-263, 331-333, 371-373, 396-398, 419-421, 455-457 */
+static const int KFLOPS[NKER] = {6, 14, 11, 23, 26, 39, 26, 26, 25, 22, 15, 51, 20, 29, 35, 41};  /* + :225-227, 261-263, 331-333, 371-373, 396-398, 419-421, 455-457 */
 static const char* KNAMES[NKER] = {"Laplace3D-FxU", "Laplace3D-DxU", "Laplace3D-FxdU", "Stokes3D-FxU", "Stokes3D-DxU", "Stokes3D-FxT", "Stokes3D-FSxU",
-                                   "Stokes3D-FxUP", "Laplace3D-Fxd2U", "Laplace3D-DxdU", "BiotSavart3D-FxU", "BiotSavart3D-FxdU"};
+                                   "Stokes3D-FxUP", "Laplace3D-Fxd2U", "Laplace3D-DxdU", "BiotSavart3D-FxU", "BiotSavart3D-FxdU",
+                                   "Helmholtz3D-FxU", "Helmholtz3D-DxU", "Helmholtz3D-FxdU", "HelmholtzDiff3D-FxdU"};
 
 #define ORACLE_PI 3.14159265358979323846264338327950288L
 
@@ -35,8 +37,8 @@ static const char* KNAMES[NKER] = {"Laplace3D-FxU", "Laplace3D-DxU", "Laplace3D-
 static double scale_factor_f64(int kid) {
   const double pi = (double)ORACLE_PI;
   switch (kid) {
-    case 0: case 1: case 8: case 9: case 10: return 1 / (4 * pi);
-    case 2: case 11: return -1 / (4 * pi);
+    case 0: case 1: case 8: case 9: case 10: case 12: case 14: case 15: return 1 / (4 * pi);
+    case 2: case 11: case 13: return -1 / (4 * pi);  /* Helmholtz3D_DxU: kernel_functions.hpp:543-545 */
     case 3: case 6: case 7: return 1 / (8 * pi);
     case 5: return -3 / (4 * pi);  /* kernel_functions.hpp:228-230 */
     default: return 3 / (4 * pi);
@@ -45,8 +47,8 @@ static double scale_factor_f64(int kid) {
 static float scale_factor_f32(int kid) {
   const float pi = (float)ORACLE_PI;
   switch (kid) {
-    case 0: case 1: case 8: case 9: case 10: return 1 / (4 * pi);
-    case 2: case 11: return -1 / (4 * pi);
+    case 0: case 1: case 8: case 9: case 10: case 12: case 14: case 15: return 1 / (4 * pi);
+    case 2: case 11: case 13: return -1 / (4 * pi);  /* Helmholtz3D_DxU: kernel_functions.hpp:543-545 */
     case 3: case 6: case 7: return 1 / (8 * pi);
     case 5: return -3 / (4 * pi);  /* kernel_functions.hpp:228-230 */
     default: return 3 / (4 * pi);
@@ -58,32 +60,39 @@ static float scale_factor_f32(int kid) {
 
 #define REAL double
 #define SQRT sqrt
+#define SIN sin
+#define COS cos
 #define FN(name) CAT(name, _f64)
 #include "sctl_oracle_impl.h"
 #undef REAL
 #undef SQRT
 #undef FN
 
+#undef SIN
+#undef COS
 #define REAL float
 #define SQRT sqrtf
+#define SIN sinf
+#define COS cosf
 #define FN(name) CAT(name, _f32)
 #include "sctl_oracle_impl.h"
 #undef REAL
 #undef SQRT
 #undef FN
 
-int oracle_eval(int kernel_id, int real_bytes, int omp, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg) {
+/* mu: kernel context (Helmholtz wavenumber, kernel_functions.hpp:484-488); ignored by the other kernels */
+int oracle_eval(int kernel_id, int real_bytes, int omp, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, double mu) {
   if (kernel_id < 0 || kernel_id >= NKER) return 1;
-  if (real_bytes == 8) eval_f64(kernel_id, omp, Ns, Nt, (const double*)r_src, (const double*)n_src, (const double*)v_src, (const double*)r_trg, (double*)v_trg);
-  else if (real_bytes == 4) eval_f32(kernel_id, omp, Ns, Nt, (const float*)r_src, (const float*)n_src, (const float*)v_src, (const float*)r_trg, (float*)v_trg);
+  if (real_bytes == 8) eval_f64(kernel_id, omp, Ns, Nt, (const double*)r_src, (const double*)n_src, (const double*)v_src, (const double*)r_trg, (double*)v_trg, mu);
+  else if (real_bytes == 4) eval_f32(kernel_id, omp, Ns, Nt, (const float*)r_src, (const float*)n_src, (const float*)v_src, (const float*)r_trg, (float*)v_trg, (float)mu);
   else return 3;
   return 0;
 }
 
-int oracle_kernel_matrix(int kernel_id, int real_bytes, int omp, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM) {
+int oracle_kernel_matrix(int kernel_id, int real_bytes, int omp, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, double mu) {
   if (kernel_id < 0 || kernel_id >= NKER) return 1;
-  if (real_bytes == 8) kernel_matrix_f64(kernel_id, omp, Ns, Nt, (const double*)r_src, (const double*)n_src, (const double*)r_trg, (double*)M, ldM);
-  else if (real_bytes == 4) kernel_matrix_f32(kernel_id, omp, Ns, Nt, (const float*)r_src, (const float*)n_src, (const float*)r_trg, (float*)M, ldM);
+  if (real_bytes == 8) kernel_matrix_f64(kernel_id, omp, Ns, Nt, (const double*)r_src, (const double*)n_src, (const double*)r_trg, (double*)M, ldM, mu);
+  else if (real_bytes == 4) kernel_matrix_f32(kernel_id, omp, Ns, Nt, (const float*)r_src, (const float*)n_src, (const float*)r_trg, (float*)M, ldM, (float)mu);
   else return 3;
   return 0;
 }

@@ -8,8 +8,8 @@ static inline REAL FN(rsqrt_masked)(REAL r2) { return r2 > 0 ? (REAL)1 / SQRT(r2
 
 /* One source-target pair: dX = xt - xs (generic-kernel.txx:108-109), then the micro-kernel.
  * vt is the UNSCALED accumulator (scale applied once at the end, generic-kernel.txx:204-208). */
-static inline void FN(pair_matrix)(int kid, REAL* u, const REAL* r, const REAL* ns);
-static inline void FN(pair_apply)(int kid, REAL* vt, const REAL* xt, const REAL* xs, const REAL* ns, const REAL* f) {
+static inline void FN(pair_matrix)(int kid, REAL* u, const REAL* r, const REAL* ns, REAL mu);
+static inline void FN(pair_apply)(int kid, REAL* vt, const REAL* xt, const REAL* xs, const REAL* ns, const REAL* f, REAL mu) {
   REAL r[3];
   for (int k = 0; k < 3; k++) r[k] = xt[k] - xs[k];
   const REAL r2 = r[0]*r[0] + r[1]*r[1] + r[2]*r[2];
@@ -60,10 +60,10 @@ static inline void FN(pair_apply)(int kid, REAL* vt, const REAL* xt, const REAL*
       for (int i = 0; i < 3; i++) vt[i] += f[i]*rinv + r[i]*t;
       vt[3] += t;
     } break;
-    case 8: case 9: case 11: { /* no fused apply: uKerMatrix then FMA, generic-kernel.txx:113-119 */
+    case 8: case 9: case 11: case 15: { /* no fused apply: uKerMatrix then FMA, generic-kernel.txx:113-119 */
       REAL u[27];
       const int K0 = KDIMS[kid][0], K1 = KDIMS[kid][1];
-      FN(pair_matrix)(kid, u, r, ns);
+      FN(pair_matrix)(kid, u, r, ns, mu);
       for (int k0 = 0; k0 < K0; k0++) for (int k1 = 0; k1 < K1; k1++) vt[k1] = u[k0*K1+k1] * f[k0] + vt[k1];
     } break;
     case 10: { /* BiotSavart3D_FxU fused apply: kernel_functions.hpp:436-447 */
@@ -72,12 +72,35 @@ static inline void FN(pair_apply)(int kid, REAL* vt, const REAL* xt, const REAL*
       vt[1] += (f[2]*r[0] - r[2]*f[0]) * rinv3;
       vt[2] += (f[0]*r[1] - r[0]*f[1]) * rinv3;
     } break;
+    case 12: { /* Helmholtz3D_FxU fused apply: kernel_functions.hpp:519-532 */
+      const REAL arg = r2 * rinv * mu, sn = SIN(arg), cs = COS(arg);
+      const REAL G0 = cs * rinv, G1 = sn * rinv;
+      vt[0] += f[0]*G0 - f[1]*G1;
+      vt[1] += f[0]*G1 + f[1]*G0;
+    } break;
+    case 13: { /* Helmholtz3D_DxU fused apply: kernel_functions.hpp:561-577 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL ndotr = ns[0]*r[0] + ns[1]*r[1] + ns[2]*r[2];
+      const REAL arg = r2 * rinv * mu, sn = SIN(arg), cs = COS(arg);
+      const REAL G0 = (-mu*sn - cs * rinv) * rinv2 * ndotr;
+      const REAL G1 = ( mu*cs - sn * rinv) * rinv2 * ndotr;
+      vt[0] += f[0]*G0 - f[1]*G1;
+      vt[1] += f[0]*G1 + f[1]*G0;
+    } break;
+    case 14: { /* Helmholtz3D_FxdU fused apply: kernel_functions.hpp:607-626 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL arg = r2 * rinv * mu, sn = SIN(arg), cs = COS(arg);
+      const REAL G0 = (-mu*sn - cs * rinv) * rinv2;
+      const REAL G1 = ( mu*cs - sn * rinv) * rinv2;
+      const REAL fG0 = f[0]*G0 - f[1]*G1, fG1 = f[0]*G1 + f[1]*G0;
+      for (int i = 0; i < 3; i++) { vt[i*2+0] += fG0 * r[i]; vt[i*2+1] += fG1 * r[i]; }
+    } break;
   }
 }
 
 /* uKerMatrix for one displacement r (= xt - xs): kernel_functions.hpp:43-47, 72-78, 92-99, 136-145, 191-202.
  * u is K0 x K1 row-major, unscaled. */
-static inline void FN(pair_matrix)(int kid, REAL* u, const REAL* r, const REAL* ns) {
+static inline void FN(pair_matrix)(int kid, REAL* u, const REAL* r, const REAL* ns, REAL mu) {
   const REAL r2 = r[0]*r[0] + r[1]*r[1] + r[2]*r[2];
   const REAL rinv = FN(rsqrt_masked)(r2);
   switch (kid) {
@@ -151,27 +174,56 @@ static inline void FN(pair_matrix)(int kid, REAL* u, const REAL* r, const REAL* 
       U[0][7] = -rinv3 +t5*r[1]*r[1]; U[1][7] =        -t5*r[0]*r[1]; U[2][7] =                    Z;
       U[0][8] =         t5*r[1]*r[2]; U[1][8] =        -t5*r[0]*r[2]; U[2][8] =                    Z;
     } break;
+    case 12: { /* Helmholtz3D_FxU: kernel_functions.hpp:506-516 */
+      const REAL arg = r2 * rinv * mu, sn = SIN(arg), cs = COS(arg);
+      u[0] = cs * rinv; u[1] = sn * rinv; u[2] = -u[1]; u[3] = u[0];
+    } break;
+    case 13: { /* Helmholtz3D_DxU: kernel_functions.hpp:546-558 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL ndotr = ns[0]*r[0] + ns[1]*r[1] + ns[2]*r[2];
+      const REAL arg = r2 * rinv * mu, sn = SIN(arg), cs = COS(arg);
+      u[0] = (-mu*sn - cs * rinv) * rinv2 * ndotr;
+      u[1] = ( mu*cs - sn * rinv) * rinv2 * ndotr;
+      u[2] = -u[1]; u[3] = u[0];
+    } break;
+    case 14: { /* Helmholtz3D_FxdU: kernel_functions.hpp:591-604 */
+      const REAL rinv2 = rinv * rinv;
+      const REAL arg = r2 * rinv * mu, sn = SIN(arg), cs = COS(arg);
+      const REAL G0 = (-mu*sn - cs * rinv) * rinv2;
+      const REAL G1 = ( mu*cs - sn * rinv) * rinv2;
+      for (int i = 0; i < 3; i++) { u[i*2+0] = G0 * r[i]; u[i*2+1] = G1 * r[i]; u[6+i*2+0] = -u[i*2+1]; u[6+i*2+1] = u[i*2+0]; }
+    } break;
+    case 15: { /* HelmholtzDiff3D_FxdU: kernel_functions.hpp:640-656 (half-angle form) */
+      const REAL rinv2 = rinv * rinv;
+      const REAL arg = r2 * rinv * mu * (REAL)0.5, sh = SIN(arg), ch = COS(arg);
+      const REAL sn = (REAL)2 * sh * ch;
+      const REAL cm1 = -(REAL)2 * sh * sh;
+      const REAL cs = (REAL)1 + cm1;
+      const REAL G0 = (-mu*sn - cm1 * rinv) * rinv2;
+      const REAL G1 = ( mu*cs - sn  * rinv) * rinv2;
+      for (int i = 0; i < 3; i++) { u[i*2+0] = G0 * r[i]; u[i*2+1] = G1 * r[i]; u[6+i*2+0] = -u[i*2+1]; u[6+i*2+1] = u[i*2+0]; }
+    } break;
   }
 }
 
 /* GenericKernel::Eval, generic-kernel.txx:102-211.  Per target: zero accumulator (:179), sources in
  * index order (:181-186), then v_trg[t*K1+k] += acc[k] * scale (:204-208) -- ACCUMULATES into v_trg
  * (the caller-side ReInit+SetZero on a size mismatch, :129-132, is the wrapper's job). */
-static void FN(eval)(int kid, int omp, int64_t Ns, int64_t Nt, const REAL* r_src, const REAL* n_src, const REAL* v_src, const REAL* r_trg, REAL* v_trg) {
+static void FN(eval)(int kid, int omp, int64_t Ns, int64_t Nt, const REAL* r_src, const REAL* n_src, const REAL* v_src, const REAL* r_trg, REAL* v_trg, REAL mu) {
   const int K0 = KDIMS[kid][0], K1 = KDIMS[kid][1], ND = KDIMS[kid][2];
   const REAL scale = (REAL)FN(scale_factor)(kid);
   #pragma omp parallel for schedule(static) if (omp)
   for (int64_t t = 0; t < Nt; t++) {
     REAL acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int64_t s = 0; s < Ns; s++)
-      FN(pair_apply)(kid, acc, r_trg + t*3, r_src + s*3, ND ? n_src + s*ND : (const REAL*)0, v_src + s*K0);
+      FN(pair_apply)(kid, acc, r_trg + t*3, r_src + s*3, ND ? n_src + s*ND : (const REAL*)0, v_src + s*K0, mu);
     for (int k = 0; k < K1; k++) v_trg[t*K1 + k] += acc[k] * scale;
   }
 }
 
 /* GenericKernel::KernelMatrix, generic-kernel.txx:213-329: M[(s*K0+k0)][(t*K1+k1)] = u[k0][k1] * scale,
  * OVERWRITES (:268,306), row-major (Ns*K0) x (Nt*K1) with leading dimension ldM. */
-static void FN(kernel_matrix)(int kid, int omp, int64_t Ns, int64_t Nt, const REAL* r_src, const REAL* n_src, const REAL* r_trg, REAL* M, int64_t ldM) {
+static void FN(kernel_matrix)(int kid, int omp, int64_t Ns, int64_t Nt, const REAL* r_src, const REAL* n_src, const REAL* r_trg, REAL* M, int64_t ldM, REAL mu) {
   const int K0 = KDIMS[kid][0], K1 = KDIMS[kid][1], ND = KDIMS[kid][2];
   const REAL scale = (REAL)FN(scale_factor)(kid);
   #pragma omp parallel for schedule(static) if (omp)
@@ -179,7 +231,7 @@ static void FN(kernel_matrix)(int kid, int omp, int64_t Ns, int64_t Nt, const RE
     for (int64_t t = 0; t < Nt; t++) {
       REAL r[3], u[27];
       for (int k = 0; k < 3; k++) r[k] = r_trg[t*3+k] - r_src[s*3+k];
-      FN(pair_matrix)(kid, u, r, ND ? n_src + s*ND : (const REAL*)0);
+      FN(pair_matrix)(kid, u, r, ND ? n_src + s*ND : (const REAL*)0, mu);
       for (int k0 = 0; k0 < K0; k0++) for (int k1 = 0; k1 < K1; k1++) M[(s*K0+k0)*ldM + t*K1+k1] = u[k0*K1+k1] * scale;
     }
   }

@@ -20,7 +20,8 @@ LIB_PATH = os.path.join(_HERE, "libsctl_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "sctl_cuda.h")
 
 KERNEL_IDS = {"Laplace3D_FxU": 0, "Laplace3D_DxU": 1, "Laplace3D_FxdU": 2, "Stokes3D_FxU": 3, "Stokes3D_DxU": 4, "Stokes3D_FxT": 5, "Stokes3D_FSxU": 6,
-              "Stokes3D_FxUP": 7, "Laplace3D_Fxd2U": 8, "Laplace3D_DxdU": 9, "BiotSavart3D_FxU": 10, "BiotSavart3D_FxdU": 11}
+              "Stokes3D_FxUP": 7, "Laplace3D_Fxd2U": 8, "Laplace3D_DxdU": 9, "BiotSavart3D_FxU": 10, "BiotSavart3D_FxdU": 11,
+              "Helmholtz3D_FxU": 12, "Helmholtz3D_DxU": 13, "Helmholtz3D_FxdU": 14, "HelmholtzDiff3D_FxdU": 15}
 
 _lib = None
 
@@ -45,9 +46,9 @@ def load_library():
     L.sctl_cuda_last_error.restype = C.c_char_p
     L.sctl_cuda_kernel_info.argtypes = [i, ip, ip, ip, ip, ip, dp, C.POINTER(C.c_char_p)]
     L.sctl_cuda_eval.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, vp, vp, i64]
-    L.sctl_cuda_kernel_matrix.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, i64]
-    L.sctl_cuda_eval_device.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, vp, vp]
-    L.sctl_cuda_kernel_matrix_device.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, i64, vp]
+    L.sctl_cuda_kernel_matrix.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, i64, vp, i64]
+    L.sctl_cuda_eval_device.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]
+    L.sctl_cuda_kernel_matrix_device.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]
     L.sctl_cuda_rsqrt_device.argtypes = [i, i, i64, vp, vp, vp]
     L.sctl_cuda_last_timing.argtypes = [dp, dp, dp]
     L.sctl_cuda_last_plan.argtypes = [ip, ip, ip, ip, ip, ip, dp]
@@ -144,10 +145,19 @@ def _real_bytes_of(t):
     return 8 if "64" in str(t.dtype) else 4
 
 
-def eval_device(kernel, d_r_src, d_n_src, d_v_src, d_r_trg, d_v_trg, digits=-1, stream=None, Ns=None, Nt=None, real_bytes=None):
+def _ctx_buf(ctx, real_bytes):
+    if ctx is None:
+        return None, 0
+    buf = np.array([ctx], dtype=np.float64 if real_bytes == 8 else np.float32)
+    return buf, buf.itemsize
+
+
+def eval_device(kernel, d_r_src, d_n_src, d_v_src, d_r_trg, d_v_trg, digits=-1, stream=None, Ns=None, Nt=None, real_bytes=None, ctx=None):
     """sctl_cuda_eval_device on torch CUDA tensors (or raw device addresses): d_v_trg += K * d_v_src, asynchronous."""
     L = load_library()
     kid = _kid(kernel)
+    if ctx is None and isinstance(kernel, GenericKernel):
+        ctx = kernel.GetCtxPtr()
     if Ns is None:
         Ns = d_r_src.numel() // 3
     if Nt is None:
@@ -157,13 +167,16 @@ def eval_device(kernel, d_r_src, d_n_src, d_v_src, d_r_trg, d_v_trg, digits=-1, 
     if stream is None:
         import torch
         stream = torch.cuda.current_stream().cuda_stream
+    cbuf, nb = _ctx_buf(ctx, real_bytes)
     _check(L.sctl_cuda_eval_device(kid, real_bytes, int(digits), int(Ns), int(Nt), _dev_ptr(d_r_src), _dev_ptr(d_n_src), _dev_ptr(d_v_src),
-                                   _dev_ptr(d_r_trg), _dev_ptr(d_v_trg), C.c_void_p(stream)))
+                                   _dev_ptr(d_r_trg), _dev_ptr(d_v_trg), _np_ptr(cbuf), nb, C.c_void_p(stream)))
 
 
-def kernel_matrix_device(kernel, d_r_src, d_n_src, d_r_trg, d_M, digits=-1, stream=None, ldM=None):
+def kernel_matrix_device(kernel, d_r_src, d_n_src, d_r_trg, d_M, digits=-1, stream=None, ldM=None, ctx=None):
     L = load_library()
     kid = _kid(kernel)
+    if ctx is None and isinstance(kernel, GenericKernel):
+        ctx = kernel.GetCtxPtr()
     Ns, Nt = d_r_src.numel() // 3, d_r_trg.numel() // 3
     info = kernel_info(kid)
     if ldM is None:
@@ -171,8 +184,9 @@ def kernel_matrix_device(kernel, d_r_src, d_n_src, d_r_trg, d_M, digits=-1, stre
     if stream is None:
         import torch
         stream = torch.cuda.current_stream().cuda_stream
+    cbuf, nb = _ctx_buf(ctx, _real_bytes_of(d_r_src))
     _check(L.sctl_cuda_kernel_matrix_device(kid, _real_bytes_of(d_r_src), int(digits), Ns, Nt, _dev_ptr(d_r_src), _dev_ptr(d_n_src), _dev_ptr(d_r_trg),
-                                            _dev_ptr(d_M), int(ldM), C.c_void_p(stream)))
+                                            _dev_ptr(d_M), int(ldM), _np_ptr(cbuf), nb, C.c_void_p(stream)))
 
 
 def rsqrt_device(d_x, d_y, digits=-1, stream=None):
@@ -196,6 +210,8 @@ class GenericKernel:
         # kernel_functions.hpp:220-483
         5: (3, 9, 0, 39, "Stokes3D-FxT"), 6: (4, 3, 0, 26, "Stokes3D-FSxU"), 7: (3, 4, 0, 26, "Stokes3D-FxUP"), 8: (1, 9, 0, 25, "Laplace3D-Fxd2U"),
         9: (1, 3, 3, 22, "Laplace3D-DxdU"), 10: (3, 3, 0, 15, "BiotSavart3D-FxU"), 11: (3, 9, 0, 51, "BiotSavart3D-FxdU"),
+        # Helmholtz (:490-659): complex values as (re, im) pairs; SetCtxPtr(wavenumber)
+        12: (2, 2, 0, 20, "Helmholtz3D-FxU"), 13: (2, 2, 3, 29, "Helmholtz3D-DxU"), 14: (2, 6, 0, 35, "Helmholtz3D-FxdU"), 15: (2, 6, 0, 41, "HelmholtzDiff3D-FxdU"),
     }
 
     def __init__(self, kernel):
@@ -222,7 +238,15 @@ class GenericKernel:
         return self._flops
 
     def SetCtxPtr(self, ctx):
+        """Kernel context (generic-kernel.hpp:79).  For the Helmholtz kernels: the wavenumber (a Python float; the
+        reference takes a pointer to one Real of the evaluation type, kernel_functions.hpp:484-488)."""
         self._ctx = ctx
+
+    def _ctx_arg(self, dtype):
+        if self._ctx is None:
+            return None, 0
+        buf = np.array([self._ctx], dtype=dtype)
+        return buf, buf.itemsize
 
     def GetCtxPtr(self):
         return self._ctx
@@ -231,7 +255,8 @@ class GenericKernel:
         pi = dtype(np.pi)
         one = dtype(1)
         return {0: one / (4 * pi), 1: one / (4 * pi), 2: -one / (4 * pi), 3: one / (8 * pi), 4: dtype(3) / (4 * pi), 5: dtype(-3) / (4 * pi), 6: one / (8 * pi),
-                7: one / (8 * pi), 8: one / (4 * pi), 9: one / (4 * pi), 10: one / (4 * pi), 11: -one / (4 * pi)}[self.kernel_id]
+                7: one / (8 * pi), 8: one / (4 * pi), 9: one / (4 * pi), 10: one / (4 * pi), 11: -one / (4 * pi), 12: one / (4 * pi), 13: -one / (4 * pi),
+                14: one / (4 * pi), 15: one / (4 * pi)}[self.kernel_id]
 
     def _arrays(self, r_trg, r_src, n_src, v_src, dtype, need_v=True):
         r_trg = np.ascontiguousarray(r_trg, dtype=dtype).reshape(-1)
@@ -267,8 +292,9 @@ class GenericKernel:
         flat = out.reshape(-1)
         if digits >= 16:
             digits = -1  # generic-kernel.txx:97
+        ctx, nb = self._ctx_arg(dtype)
         _check(load_library().sctl_cuda_eval(self.kernel_id, flat.itemsize, int(digits), Ns, Nt, _np_ptr(r_src), _np_ptr(n_src), _np_ptr(v_src),
-                                             _np_ptr(r_trg), _np_ptr(flat), None, 0))
+                                             _np_ptr(r_trg), _np_ptr(flat), _np_ptr(ctx), nb))
         return out
 
     def KernelMatrix(self, Xt, Xs, Xn, digits=-1, dtype=None, M=None):
@@ -279,7 +305,8 @@ class GenericKernel:
         rows, cols = Ns * self._k0, Nt * self._k1
         if M is None or M.shape != (rows, cols) or M.dtype != dtype or not M.flags.c_contiguous:
             M = np.zeros((rows, cols), dtype=dtype)  # ReInit + SetZero (:220-223)
-        _check(load_library().sctl_cuda_kernel_matrix(self.kernel_id, M.itemsize, int(digits), Ns, Nt, _np_ptr(Xs), _np_ptr(Xn), _np_ptr(Xt), _np_ptr(M), cols))
+        ctx, nb = self._ctx_arg(dtype)
+        _check(load_library().sctl_cuda_kernel_matrix(self.kernel_id, M.itemsize, int(digits), Ns, Nt, _np_ptr(Xs), _np_ptr(Xn), _np_ptr(Xt), _np_ptr(M), cols, _np_ptr(ctx), nb))
         return M
 
 
@@ -295,4 +322,8 @@ Laplace3D_Fxd2U = GenericKernel("Laplace3D_Fxd2U")
 Laplace3D_DxdU = GenericKernel("Laplace3D_DxdU")
 BiotSavart3D_FxU = GenericKernel("BiotSavart3D_FxU")
 BiotSavart3D_FxdU = GenericKernel("BiotSavart3D_FxdU")
+Helmholtz3D_FxU = GenericKernel("Helmholtz3D_FxU")  # SetCtxPtr(wavenumber) before Eval
+Helmholtz3D_DxU = GenericKernel("Helmholtz3D_DxU")
+Helmholtz3D_FxdU = GenericKernel("Helmholtz3D_FxdU")
+HelmholtzDiff3D_FxdU = GenericKernel("HelmholtzDiff3D_FxdU")
 KERNELS = {name: GenericKernel(name) for name in KERNEL_IDS}

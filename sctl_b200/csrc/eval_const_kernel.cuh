@@ -38,6 +38,7 @@ template <class Real> struct ConstEvalArgs {
   int sub_len;        // records per cluster rank (grid.y slice)
   int allow_unmasked; // this call ran the coincidence probe: c_eval_must_mask is meaningful
   Real scale;
+  Real ctx0;          // kernel context by value (Helmholtz wavenumber)
 };
 
 template <class Real, int KID> constexpr int const_chunk_records() { return CONST_PACK_BYTES / (RecTraits<Real, KID>::REC * (int)sizeof(Real)); }
@@ -68,14 +69,14 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
     for (int s = 0; s < n; s++) {
       const Real* rec = src + s * REC;  // uniform address: LDCU into uniform registers
 #pragma unroll
-      for (int j = 0; j < T; j++) pair_update<KID, RSQ, false>(acc[j], xt[j], rec);
+      for (int j = 0; j < T; j++) pair_update<KID, RSQ, false>(acc[j], xt[j], rec, a.ctx0);
     }
   } else {
 #pragma unroll U
     for (int s = 0; s < n; s++) {
       const Real* rec = src + s * REC;
 #pragma unroll
-      for (int j = 0; j < T; j++) pair_update<KID, RSQ, true>(acc[j], xt[j], rec);
+      for (int j = 0; j < T; j++) pair_update<KID, RSQ, true>(acc[j], xt[j], rec, a.ctx0);
     }
   }
   if (gridDim.y > 1) {

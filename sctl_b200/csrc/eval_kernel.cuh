@@ -87,9 +87,9 @@ __global__ void pack_sources_kernel(int64_t Ns, const Real* __restrict__ r_src, 
     } else {
 #pragma unroll
       for (int k = 0; k < K0; k++) rec[3 + k] = v_src[s * K0 + k];
-      if (KID == STOKES3D_DXU) {
+      if (KID == STOKES3D_DXU || KID == HELMHOLTZ3D_DXU) {  // normals follow the densities
 #pragma unroll
-        for (int k = 0; k < 3; k++) rec[6 + k] = n_src[s * 3 + k];
+        for (int k = 0; k < 3; k++) rec[3 + K0 + k] = n_src[s * 3 + k];
       }
     }
 #pragma unroll
@@ -110,6 +110,7 @@ template <class Real> struct EvalArgs {
   int n_split;
   Real scale;
   const int* must_mask;  // device flag from coincidence_probe_kernel (nullptr: always mask r2 == 0 pairs)
+  Real ctx0;             // kernel context by value (Helmholtz wavenumber); 0 otherwise
 };
 
 template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES> struct EvalConfig {
@@ -128,7 +129,7 @@ template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAG
 
 // One tile of packed records against this thread's T register-resident targets.
 template <class Real, int KID, int T, int R, int RSQ, int U, bool MASK>
-__device__ __forceinline__ void consume_tile(const Real* tile, int n, int rep, Real (&acc)[T][KerTraits<KID>::K1], const Real (&xt)[T][3]) {
+__device__ __forceinline__ void consume_tile(const Real* tile, int n, int rep, Real (&acc)[T][KerTraits<KID>::K1], const Real (&xt)[T][3], Real mu) {
   constexpr int REC = RecTraits<Real, KID>::REC;
   constexpr int W = 16 / (int)sizeof(Real);
   using Vec16 = typename std::conditional<sizeof(Real) == 8, double2, float4>::type;
@@ -143,7 +144,7 @@ __device__ __forceinline__ void consume_tile(const Real* tile, int n, int rep, R
       for (int c = 0; c < W; c++) rec[q * W + c] = ((const Real*)&v)[c];
     }
 #pragma unroll
-    for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec);
+    for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, mu);
   }
 }
 
@@ -214,8 +215,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const E
     const Real* tile = ring + st * Cfg::STAGE_REALS;
     const int64_t rem = n_src - (int64_t)i * TILE;
     const int n = (int)(rem < TILE ? rem : TILE);
-    if (unmasked) consume_tile<Real, KID, T, R, RSQ, U, false>(tile, n, rep, acc, xt);
-    else consume_tile<Real, KID, T, R, RSQ, U, true>(tile, n, rep, acc, xt);
+    if (unmasked) consume_tile<Real, KID, T, R, RSQ, U, false>(tile, n, rep, acc, xt, a.ctx0);
+    else consume_tile<Real, KID, T, R, RSQ, U, true>(tile, n, rep, acc, xt, a.ctx0);
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
   }

@@ -13,7 +13,7 @@ namespace sctl_cuda {
 
 template <class Real, int KID, int RSQ, int BT>
 __global__ void __launch_bounds__(BT) kernel_matrix_kernel(int64_t Ns, int64_t Nt, const Real* __restrict__ r_src, const Real* __restrict__ n_src,
-                                                         const Real* __restrict__ r_trg, Real* __restrict__ M, int64_t ldM, Real scale) {
+                                                         const Real* __restrict__ r_trg, Real* __restrict__ M, int64_t ldM, Real scale, Real mu) {
   constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
   __shared__ Real stage[K0][BT * K1 + 1];
   const int64_t t_blk = (int64_t)blockIdx.x * BT;
@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(BT) kernel_matrix_kernel(int64_t Ns, int64_t N
     const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
     const Real rinv = rsqrt_masked<RSQ>(r2);
     Real u[K0 * K1];
-    PairMatrix<KID, Real>::run(u, dx, rinv, n);
+    if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u, dx, rinv, n, r2, mu);
+    else PairMatrix<KID, Real>::run(u, dx, rinv, n);
     if (K1 == 1) {
       // one entry per (row, target): the direct store is already coalesced
       if (t < Nt) {

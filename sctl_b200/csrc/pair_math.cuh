@@ -18,8 +18,11 @@ namespace sctl_cuda {
 enum : int {
   LAPLACE3D_FXU = 0, LAPLACE3D_DXU = 1, LAPLACE3D_FXDU = 2, STOKES3D_FXU = 3, STOKES3D_DXU = 4,
   STOKES3D_FXT = 5, STOKES3D_FSXU = 6, STOKES3D_FXUP = 7, LAPLACE3D_FXD2U = 8, LAPLACE3D_DXDU = 9, BIOTSAVART3D_FXU = 10, BIOTSAVART3D_FXDU = 11,
-  NUM_KERNELS = 12
+  // 12-15: the Helmholtz kernels; their context (ctx_ptr) is the wavenumber, passed to the device by value
+  HELMHOLTZ3D_FXU = 12, HELMHOLTZ3D_DXU = 13, HELMHOLTZ3D_FXDU = 14, HELMHOLTZDIFF3D_FXDU = 15,
+  NUM_KERNELS = 16
 };
+template <int KID> struct KerNeedsCtx { static constexpr bool value = (KID >= HELMHOLTZ3D_FXU); };
 
 // How far the seed is refined; chosen on the host from `digits` (see rsq_mode_for_digits()).
 enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
@@ -87,6 +90,11 @@ template <> struct KerTraits<LAPLACE3D_FXD2U>   { static constexpr int K0 = 1, K
 template <> struct KerTraits<LAPLACE3D_DXDU>    { static constexpr int K0 = 1, K1 = 3, ND = 3, PACK = 6, FLOPS = 22, F_ALG = 30; };
 template <> struct KerTraits<BIOTSAVART3D_FXU>  { static constexpr int K0 = 3, K1 = 3, ND = 0, PACK = 6, FLOPS = 15, F_ALG = 26; };
 template <> struct KerTraits<BIOTSAVART3D_FXDU> { static constexpr int K0 = 3, K1 = 9, ND = 0, PACK = 6, FLOPS = 51, F_ALG = 52; };
+// kernel_functions.hpp:490-659; complex values as adjacent (re, im) pairs; sincos counted as 2 flop in F_ALG
+template <> struct KerTraits<HELMHOLTZ3D_FXU>      { static constexpr int K0 = 2, K1 = 2, ND = 0, PACK = 5, FLOPS = 20, F_ALG = 24; };
+template <> struct KerTraits<HELMHOLTZ3D_DXU>      { static constexpr int K0 = 2, K1 = 2, ND = 3, PACK = 8, FLOPS = 29, F_ALG = 38; };
+template <> struct KerTraits<HELMHOLTZ3D_FXDU>     { static constexpr int K0 = 2, K1 = 6, ND = 0, PACK = 5, FLOPS = 35, F_ALG = 44; };
+template <> struct KerTraits<HELMHOLTZDIFF3D_FXDU> { static constexpr int K0 = 2, K1 = 6, ND = 0, PACK = 5, FLOPS = 41, F_ALG = 50; };
 
 // Reals per record, padded so that every record is a whole number of 16-byte words (LDS.128 / bulk-copy unit).
 template <class Real, int KID> struct RecTraits {
@@ -109,6 +117,10 @@ __host__ inline KernelInfo kernel_info(int kid) {
     case LAPLACE3D_DXDU:    return {1, 3, 3, 22, 30, "Laplace3D-DxdU"};
     case BIOTSAVART3D_FXU:  return {3, 3, 0, 15, 26, "BiotSavart3D-FxU"};
     case BIOTSAVART3D_FXDU: return {3, 9, 0, 51, 52, "BiotSavart3D-FxdU"};
+    case HELMHOLTZ3D_FXU:      return {2, 2, 0, 20, 24, "Helmholtz3D-FxU"};
+    case HELMHOLTZ3D_DXU:      return {2, 2, 3, 29, 38, "Helmholtz3D-DxU"};
+    case HELMHOLTZ3D_FXDU:     return {2, 6, 0, 35, 44, "Helmholtz3D-FxdU"};
+    case HELMHOLTZDIFF3D_FXDU: return {2, 6, 0, 41, 50, "HelmholtzDiff3D-FxdU"};
     default:             return {0, 0, 0, 0, 0, nullptr};
   }
 }
@@ -117,8 +129,9 @@ __host__ inline KernelInfo kernel_info(int kid) {
 template <class Real> __host__ __device__ inline Real scale_factor(int kid) {
   const Real pi = (Real)3.14159265358979323846264338327950288L;
   switch (kid) {
-    case LAPLACE3D_FXU: case LAPLACE3D_DXU: case LAPLACE3D_FXD2U: case LAPLACE3D_DXDU: case BIOTSAVART3D_FXU: return 1 / (4 * pi);
-    case LAPLACE3D_FXDU: case BIOTSAVART3D_FXDU: return -1 / (4 * pi);
+    case LAPLACE3D_FXU: case LAPLACE3D_DXU: case LAPLACE3D_FXD2U: case LAPLACE3D_DXDU: case BIOTSAVART3D_FXU:
+    case HELMHOLTZ3D_FXU: case HELMHOLTZ3D_FXDU: case HELMHOLTZDIFF3D_FXDU: return 1 / (4 * pi);
+    case LAPLACE3D_FXDU: case BIOTSAVART3D_FXDU: case HELMHOLTZ3D_DXU: return -1 / (4 * pi);
     case STOKES3D_FXU: case STOKES3D_FSXU: case STOKES3D_FXUP: return 1 / (8 * pi);
     case STOKES3D_FXT: return -3 / (4 * pi);
     default: return 3 / (4 * pi);  // Stokes3D_DxU
@@ -278,16 +291,82 @@ template <class Real> struct PairApply<BIOTSAVART3D_FXDU, Real> {
   }
 };
 
+// ---- Helmholtz kernels (kernel_functions.hpp:490-659): G = exp(i mu r) / r and derivatives; record = [x y z f_re f_im (n)] ----
+__device__ __forceinline__ void sincos_real(double x, double* s, double* c) { sincos(x, s, c); }
+__device__ __forceinline__ void sincos_real(float x, float* s, float* c) { sincosf(x, s, c); }
+
+// (G0, G1) of the gradient-type kernels: (-mu sin - cos/r, mu cos - sin/r) / r^2;  DIFF subtracts the Laplace part
+// through the half-angle identity cos(x) - 1 = -2 sin^2(x/2) (:640-647)
+template <bool DIFF, class Real> __device__ __forceinline__ void helmholtz_grad_G(Real& G0, Real& G1, Real r2, Real rinv, Real mu) {
+  const Real rinv2 = rinv * rinv;
+  Real sn, cs;
+  if (DIFF) {
+    Real sh, ch;
+    sincos_real((r2 * rinv) * mu * (Real)0.5, &sh, &ch);
+    sn = (Real)2 * sh * ch;
+    const Real cm1 = (Real)-2 * sh * sh;
+    cs = (Real)1 + cm1;
+    G0 = (-mu * sn - cm1 * rinv) * rinv2;
+  } else {
+    sincos_real((r2 * rinv) * mu, &sn, &cs);
+    G0 = (-mu * sn - cs * rinv) * rinv2;
+  }
+  G1 = (mu * cs - sn * rinv) * rinv2;
+}
+template <class Real> struct PairApply<HELMHOLTZ3D_FXU, Real> {  // :519-532
+  static __device__ __forceinline__ void run_ctx(Real (&acc)[2], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+    Real sn, cs;
+    sincos_real((r2 * rinv) * mu, &sn, &cs);
+    const Real G0 = cs * rinv, G1 = sn * rinv;
+    acc[0] = fma(s[3], G0, fma(-s[4], G1, acc[0]));
+    acc[1] = fma(s[3], G1, fma(s[4], G0, acc[1]));
+  }
+};
+template <class Real> struct PairApply<HELMHOLTZ3D_DXU, Real> {  // :561-577
+  static __device__ __forceinline__ void run_ctx(Real (&acc)[2], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+    Real G0, G1;
+    helmholtz_grad_G<false>(G0, G1, r2, rinv, mu);
+    const Real ndotr = fma(dx[2], s[7], fma(dx[1], s[6], dx[0] * s[5]));
+    G0 *= ndotr;
+    G1 *= ndotr;
+    acc[0] = fma(s[3], G0, fma(-s[4], G1, acc[0]));
+    acc[1] = fma(s[3], G1, fma(s[4], G0, acc[1]));
+  }
+};
+template <bool DIFF, class Real> __device__ __forceinline__ void helmholtz_fxdu_apply(Real (&acc)[6], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+  Real G0, G1;
+  helmholtz_grad_G<DIFF>(G0, G1, r2, rinv, mu);
+  const Real fG0 = fma(s[3], G0, -(s[4] * G1));
+  const Real fG1 = fma(s[3], G1, s[4] * G0);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    acc[i * 2 + 0] = fma(fG0, dx[i], acc[i * 2 + 0]);
+    acc[i * 2 + 1] = fma(fG1, dx[i], acc[i * 2 + 1]);
+  }
+}
+template <class Real> struct PairApply<HELMHOLTZ3D_FXDU, Real> {  // :607-626
+  static __device__ __forceinline__ void run_ctx(Real (&acc)[6], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+    helmholtz_fxdu_apply<false>(acc, dx, rinv, s, r2, mu);
+  }
+};
+template <class Real> struct PairApply<HELMHOLTZDIFF3D_FXDU, Real> {  // uKerMatrix + FMA, :629-657
+  static __device__ __forceinline__ void run_ctx(Real (&acc)[6], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+    helmholtz_fxdu_apply<true>(acc, dx, rinv, s, r2, mu);
+  }
+};
+
 // One source-target pair, starting from coordinates.
+// `mu` is the kernel context (the Helmholtz wavenumber); the other kernels ignore it.
 template <int KID, int RSQ, bool MASK = true, class Real>
-__device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], const Real (&xt)[3], const Real* s) {
+__device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], const Real (&xt)[3], const Real* s, Real mu = 0) {
   Real dx[3];
   dx[0] = xt[0] - s[0];
   dx[1] = xt[1] - s[1];
   dx[2] = xt[2] - s[2];
   const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
   const Real rinv = rsqrt_masked<RSQ, MASK>(r2);
-  PairApply<KID, Real>::run(acc, dx, rinv, s);
+  if constexpr (KerNeedsCtx<KID>::value) PairApply<KID, Real>::run_ctx(acc, dx, rinv, s, r2, mu);
+  else PairApply<KID, Real>::run(acc, dx, rinv, s);
 }
 
 // uKerMatrix twin: u[K0][K1] (unscaled) for one displacement, with the raw normal (KernelMatrix path,
@@ -426,6 +505,40 @@ template <class Real> struct PairMatrix<BIOTSAVART3D_FXDU, Real> {
         }
       }
   }
+};
+
+// Helmholtz uKerMatrix twins: 2 x 2K complex-as-real blocks, u[1][*] is the rotated copy of u[0][*]
+template <class Real> struct PairMatrix<HELMHOLTZ3D_FXU, Real> {
+  static __device__ __forceinline__ void run_ctx(Real* u, const Real (&dx)[3], Real rinv, const Real* n, Real r2, Real mu) {
+    Real sn, cs;
+    sincos_real((r2 * rinv) * mu, &sn, &cs);
+    u[0] = cs * rinv; u[1] = sn * rinv;
+    u[2] = -u[1];     u[3] = u[0];
+  }
+};
+template <class Real> struct PairMatrix<HELMHOLTZ3D_DXU, Real> {
+  static __device__ __forceinline__ void run_ctx(Real* u, const Real (&dx)[3], Real rinv, const Real* n, Real r2, Real mu) {
+    Real G0, G1;
+    helmholtz_grad_G<false>(G0, G1, r2, rinv, mu);
+    const Real ndotr = fma(dx[2], n[2], fma(dx[1], n[1], dx[0] * n[0]));
+    u[0] = G0 * ndotr; u[1] = G1 * ndotr;
+    u[2] = -u[1];      u[3] = u[0];
+  }
+};
+template <bool DIFF, class Real> __device__ __forceinline__ void helmholtz_fxdu_matrix(Real* u, const Real (&dx)[3], Real rinv, Real r2, Real mu) {
+  Real G0, G1;
+  helmholtz_grad_G<DIFF>(G0, G1, r2, rinv, mu);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    u[i * 2 + 0] = G0 * dx[i];         u[i * 2 + 1] = G1 * dx[i];
+    u[6 + i * 2 + 0] = -u[i * 2 + 1];  u[6 + i * 2 + 1] = u[i * 2 + 0];
+  }
+}
+template <class Real> struct PairMatrix<HELMHOLTZ3D_FXDU, Real> {
+  static __device__ __forceinline__ void run_ctx(Real* u, const Real (&dx)[3], Real rinv, const Real* n, Real r2, Real mu) { helmholtz_fxdu_matrix<false>(u, dx, rinv, r2, mu); }
+};
+template <class Real> struct PairMatrix<HELMHOLTZDIFF3D_FXDU, Real> {
+  static __device__ __forceinline__ void run_ctx(Real* u, const Real (&dx)[3], Real rinv, const Real* n, Real r2, Real mu) { helmholtz_fxdu_matrix<true>(u, dx, rinv, r2, mu); }
 };
 
 }  // namespace sctl_cuda

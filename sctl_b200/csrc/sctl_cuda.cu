@@ -197,7 +197,7 @@ struct OccCache {
 };
 
 template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAGES, int MINB>
-int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, const int* must_mask, cudaStream_t stream, int min_chunk, int max_split) {
+int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, const int* must_mask, Real ctx0, cudaStream_t stream, int min_chunk, int max_split) {
   using Cfg = EvalConfig<Real, KID, T, NW, R, RSQ, TILE, STAGES>;
   auto kern = eval_pairs_kernel<Real, KID, T, NW, R, RSQ, TILE, STAGES, MINB>;
   static OccCache occ;
@@ -228,6 +228,7 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
   a.n_split = plan.n_split;
   a.scale = scale_factor<Real>(KID);
   a.must_mask = must_mask;
+  a.ctx0 = ctx0;
   constexpr int K1 = KerTraits<KID>::K1;
   int n_launches = 1;
   if (plan.n_split > 1) CU_TRY(cudaMallocAsync((void**)&a.partial, sizeof(Real) * (size_t)plan.n_split * Nt * K1, stream));
@@ -257,7 +258,7 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
 // (kernel boundary + cold constant cache), so the path is used only when a chunk x Nt is >= ~2 ms of work.
 
 template <class Real, int KID, int RSQ>
-int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, const int* must_mask, cudaStream_t stream) {
+int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, const int* must_mask, Real ctx0, cudaStream_t stream) {
   using Tn = Tune<Real>;
   constexpr int T = Tn::CONST_T, NT = Tn::CONST_NT;
   constexpr int REC = RecTraits<Real, KID>::REC;
@@ -272,6 +273,7 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   a.v_trg = v_trg;
   a.Nt = Nt;
   a.allow_unmasked = must_mask != nullptr;
+  a.ctx0 = ctx0;
   a.scale = scale_factor<Real>(KID);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_tb, (unsigned)cl);
@@ -311,7 +313,7 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
 }
 
 template <class Real, int KID, int RSQ>
-int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
+int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, Real ctx0, cudaStream_t stream) {
   using Tn = Tune<Real>;
   constexpr int REC = RecTraits<Real, KID>::REC;
   Real* pack = nullptr;
@@ -338,13 +340,13 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
   }
   int rc;
   if (Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || g.opt.const_fp32))
-    rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream);
+    rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream);
   else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8 && KerTraits<KID>::K1 <= 4)  // 9 accumulators x 4 targets would spill
-    rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, 8 * Tn::WIDE_TILE, 64);
+    rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream, 8 * Tn::WIDE_TILE, 64);
   else if (Nt <= g.opt.few_max_targets)
-    rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, Tn::FEW_TILE, 1024);
+    rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream, Tn::FEW_TILE, 1024);
   else
-    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, stream, 8 * Tn::TILE, 64);
+    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream, 8 * Tn::TILE, 64);
   if (table) cudaFreeAsync(table, stream);
   tl.n_launches += n_probe_launches;
   if (rc) {
@@ -357,20 +359,20 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
 }
 
 template <class Real, int KID>
-int eval_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, cudaStream_t stream) {
+int eval_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, Real ctx0, cudaStream_t stream) {
   switch (rsq_mode_for_digits<Real>(digits)) {
-    case RSQ_SEED: return eval_device_t<Real, KID, RSQ_SEED>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
-    case RSQ_NEWTON: return eval_device_t<Real, KID, RSQ_NEWTON>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+    case RSQ_SEED: return eval_device_t<Real, KID, RSQ_SEED>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
+    case RSQ_NEWTON: return eval_device_t<Real, KID, RSQ_NEWTON>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
     default:
-      if (sizeof(Real) == 4) return eval_device_t<Real, KID, RSQ_NEWTON>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
-      return eval_device_t<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON)>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+      if (sizeof(Real) == 4) return eval_device_t<Real, KID, RSQ_NEWTON>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
+      return eval_device_t<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON)>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
   }
 }
 
 template <class Real>
-int eval_device_r(int dev, int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, cudaStream_t stream) {
+int eval_device_r(int dev, int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, double ctx0, cudaStream_t stream) {
 #define SCTL_CUDA_CASE(K) \
-  case K: return eval_device_k<Real, K>(dev, digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)v_src, (const Real*)r_trg, (Real*)v_trg, stream);
+  case K: return eval_device_k<Real, K>(dev, digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)v_src, (const Real*)r_trg, (Real*)v_trg, (Real)ctx0, stream);
   switch (kid) {
     SCTL_CUDA_CASE(LAPLACE3D_FXU)
     SCTL_CUDA_CASE(LAPLACE3D_DXU)
@@ -384,6 +386,10 @@ int eval_device_r(int dev, int kid, int digits, int64_t Ns, int64_t Nt, const vo
     SCTL_CUDA_CASE(LAPLACE3D_DXDU)
     SCTL_CUDA_CASE(BIOTSAVART3D_FXU)
     SCTL_CUDA_CASE(BIOTSAVART3D_FXDU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_FXU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_DXU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_FXDU)
+    SCTL_CUDA_CASE(HELMHOLTZDIFF3D_FXDU)
     default: return fail("unknown kernel id %d", kid);
   }
 #undef SCTL_CUDA_CASE
@@ -396,21 +402,32 @@ int check_common(int kid, int real_bytes, int64_t Ns, int64_t Nt) {
   return 0;
 }
 
-int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, cudaStream_t stream) {
+// The kernel context (uKernel ctx_ptr, generic-kernel.hpp:79): for the Helmholtz kernels a HOST pointer to one Real, the
+// wavenumber (kernel_functions.hpp:484-488); copied by value into the launch.  Other kernels ignore it.
+int decode_ctx(int kid, int real_bytes, const void* ctx, int64_t ctx_bytes, double* ctx0) {
+  *ctx0 = 0;
+  if (kid < HELMHOLTZ3D_FXU) return 0;
+  if (!ctx) return fail("kernel %s needs its context: ctx must point to the wavenumber (one %s)", kernel_info(kid).name, real_bytes == 8 ? "double" : "float");
+  if (ctx_bytes != 0 && ctx_bytes != real_bytes) return fail("ctx_bytes (%lld) must equal real_bytes (%d) for kernel %s", (long long)ctx_bytes, real_bytes, kernel_info(kid).name);
+  *ctx0 = real_bytes == 8 ? *(const double*)ctx : (double)*(const float*)ctx;
+  return 0;
+}
+
+int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src, const void* r_trg, void* v_trg, double ctx0, cudaStream_t stream) {
   const KernelInfo ki = kernel_info(kid);
   tl.n_launches = 0;
   if (Ns == 0 || Nt == 0) return 0;  // nothing to add
   if (!r_src || !v_src || !r_trg || !v_trg) return fail("null array pointer");
   if (ki.nd && !n_src) return fail("kernel %s needs source normals (n_src is NULL)", ki.name);
-  if (real_bytes == 8) return eval_device_r<double>(dev, kid, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
-  return eval_device_r<float>(dev, kid, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, stream);
+  if (real_bytes == 8) return eval_device_r<double>(dev, kid, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
+  return eval_device_r<float>(dev, kid, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
 // KernelMatrix
 // ---------------------------------------------------------------------------------------------
 template <class Real, int KID>
-int kmat_device_k(int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, cudaStream_t stream) {
+int kmat_device_k(int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
   constexpr int BT = 128;
   // a CTA keeps its BT targets in registers and walks sources s = blockIdx.y, blockIdx.y + gridDim.y, ...; enough
   // CTAs to fill the machine (~32 per SM), few enough that each one amortises its target loads over many rows
@@ -419,18 +436,18 @@ int kmat_device_k(int digits, int64_t Ns, int64_t Nt, const Real* r_src, const R
   dim3 grid((unsigned)n_tb, (unsigned)std::min<int64_t>(rows, 65535));
   const Real scale = scale_factor<Real>(KID);
   switch (rsq_mode_for_digits<Real>(digits)) {
-    case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale); break;
-    case RSQ_NEWTON: kernel_matrix_kernel<Real, KID, RSQ_NEWTON, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale); break;
-    default: kernel_matrix_kernel<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON), BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale); break;
+    case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+    case RSQ_NEWTON: kernel_matrix_kernel<Real, KID, RSQ_NEWTON, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+    default: kernel_matrix_kernel<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON), BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
   }
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
 template <class Real>
-int kmat_device_r(int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, cudaStream_t stream) {
+int kmat_device_r(int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, double ctx0, cudaStream_t stream) {
 #define SCTL_CUDA_CASE(K) \
-  case K: return kmat_device_k<Real, K>(digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)r_trg, (Real*)M, ldM, stream);
+  case K: return kmat_device_k<Real, K>(digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)r_trg, (Real*)M, ldM, (Real)ctx0, stream);
   switch (kid) {
     SCTL_CUDA_CASE(LAPLACE3D_FXU)
     SCTL_CUDA_CASE(LAPLACE3D_DXU)
@@ -444,19 +461,23 @@ int kmat_device_r(int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src
     SCTL_CUDA_CASE(LAPLACE3D_DXDU)
     SCTL_CUDA_CASE(BIOTSAVART3D_FXU)
     SCTL_CUDA_CASE(BIOTSAVART3D_FXDU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_FXU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_DXU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_FXDU)
+    SCTL_CUDA_CASE(HELMHOLTZDIFF3D_FXDU)
     default: return fail("unknown kernel id %d", kid);
   }
 #undef SCTL_CUDA_CASE
 }
 
-int kmat_device_any(int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, cudaStream_t stream) {
+int kmat_device_any(int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, double ctx0, cudaStream_t stream) {
   const KernelInfo ki = kernel_info(kid);
   if (Ns == 0 || Nt == 0) return 0;
   if (!r_src || !r_trg || !M) return fail("null array pointer");
   if (ki.nd && !n_src) return fail("kernel %s needs source normals (n_src is NULL)", ki.name);
   if (ldM < Nt * ki.k1) return fail("ldM (%lld) smaller than Nt*K1 (%lld)", (long long)ldM, (long long)(Nt * ki.k1));
-  if (real_bytes == 8) return kmat_device_r<double>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, stream);
-  return kmat_device_r<float>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, stream);
+  if (real_bytes == 8) return kmat_device_r<double>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+  return kmat_device_r<float>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, ctx0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -537,7 +558,7 @@ struct DevBuf {
 
 // One GPU: upload everything, run, download the target range [t0, t1).
 int eval_host_one(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t t0, int64_t t1, const char* r_src, const char* n_src, const char* v_src,
-                  const char* r_trg, char* v_trg, bool timing) {
+                  const char* r_trg, char* v_trg, double ctx0, bool timing) {
   const KernelInfo ki = kernel_info(kid);
   const size_t rb = (size_t)real_bytes;
   const int64_t nt = t1 - t0;
@@ -554,7 +575,7 @@ int eval_host_one(int dev, int kid, int real_bytes, int digits, int64_t Ns, int6
   CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg + rb * t0 * 3, rb * nt * 3, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(d_vt.p, v_trg + rb * t0 * ki.k1, rb * nt * ki.k1, cudaMemcpyHostToDevice, st));
   if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][1], st));
-  if (eval_device_any(dev, kid, real_bytes, digits, Ns, nt, d_rs.p, d_ns.p, d_vs.p, d_rt.p, d_vt.p, st)) return 1;
+  if (eval_device_any(dev, kid, real_bytes, digits, Ns, nt, d_rs.p, d_ns.p, d_vs.p, d_rt.p, d_vt.p, ctx0, st)) return 1;
   if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][2], st));
   CU_TRY(cudaMemcpyAsync(v_trg + rb * t0 * ki.k1, d_vt.p, rb * nt * ki.k1, cudaMemcpyDeviceToHost, st));
   if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][3], st));
@@ -582,7 +603,7 @@ struct ShardResult {
 };
 
 void eval_host_shard(int p, int P, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const char* r_src, const char* n_src, const char* v_src,
-                     const char* r_trg, char* v_trg, ShardResult* res) {
+                     const char* r_trg, char* v_trg, double ctx0, ShardResult* res) {
   auto body = [&]() -> int {
     const KernelInfo ki = kernel_info(kid);
     const size_t rb = (size_t)real_bytes;
@@ -624,7 +645,7 @@ void eval_host_shard(int p, int P, int kid, int real_bytes, int digits, int64_t 
     ncclResult_t ne = g.nccl.GroupEnd();
     if (nr != ncclSuccess || ne != ncclSuccess) return fail("NCCL broadcast failed: %s", g.nccl.GetErrorString(nr != ncclSuccess ? nr : ne));
     CU_TRY(cudaEventRecord(ev[1], st));
-    if (nt && eval_device_any(p, kid, real_bytes, digits, Ns, nt, d_rs.p, d_ns.p, d_vs.p, d_rt.p, d_vt.p, st)) return 1;
+    if (nt && eval_device_any(p, kid, real_bytes, digits, Ns, nt, d_rs.p, d_ns.p, d_vs.p, d_rt.p, d_vt.p, ctx0, st)) return 1;
     CU_TRY(cudaEventRecord(ev[2], st));
     if (nt) CU_TRY(cudaMemcpyAsync(v_trg + rb * t0 * ki.k1, d_vt.p, rb * nt * ki.k1, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaEventRecord(ev[3], st));
@@ -736,26 +757,30 @@ int sctl_cuda_kernel_info(int kernel_id, int* k0, int* k1, int* nd, int* flops, 
 }
 
 int sctl_cuda_eval_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* d_r_src, const void* d_n_src, const void* d_v_src,
-                          const void* d_r_trg, void* d_v_trg, void* stream) {
+                          const void* d_r_trg, void* d_v_trg, const void* ctx, int64_t ctx_bytes, void* stream) {
   if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  double ctx0;
+  if (decode_ctx(kernel_id, real_bytes, ctx, ctx_bytes, &ctx0)) return 1;
   int dev;
   if (current_device_ready(&dev)) return 1;
-  return eval_device_any(dev, kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_v_src, d_r_trg, d_v_trg, (cudaStream_t)stream);
+  return eval_device_any(dev, kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_v_src, d_r_trg, d_v_trg, ctx0, (cudaStream_t)stream);
 }
 
 int sctl_cuda_kernel_matrix_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* d_r_src, const void* d_n_src,
-                                   const void* d_r_trg, void* d_M, int64_t ldM, void* stream) {
+                                   const void* d_r_trg, void* d_M, int64_t ldM, const void* ctx, int64_t ctx_bytes, void* stream) {
   if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  double ctx0;
+  if (decode_ctx(kernel_id, real_bytes, ctx, ctx_bytes, &ctx0)) return 1;
   int dev;
   if (current_device_ready(&dev)) return 1;
-  return kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_r_trg, d_M, ldM, (cudaStream_t)stream);
+  return kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_r_trg, d_M, ldM, ctx0, (cudaStream_t)stream);
 }
 
 int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src,
                    const void* r_trg, void* v_trg, const void* ctx, int64_t ctx_bytes) {
-  (void)ctx;
-  (void)ctx_bytes;
   if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  double ctx0;
+  if (decode_ctx(kernel_id, real_bytes, ctx, ctx_bytes, &ctx0)) return 1;
   const KernelInfo ki = kernel_info(kernel_id);
   int dev;
   if (current_device_ready(&dev)) return 1;
@@ -776,7 +801,7 @@ int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_
     std::vector<std::thread> th;
     for (int p = 0; p < P; p++)
       th.emplace_back(eval_host_shard, p, P, kernel_id, real_bytes, digits, Ns, Nt, (const char*)r_src, (const char*)n_src, (const char*)v_src,
-                      (const char*)r_trg, (char*)v_trg, &res[p]);
+                      (const char*)r_trg, (char*)v_trg, ctx0, &res[p]);
     for (auto& t : th) t.join();
     for (int p = 0; p < P; p++) {
       if (res[p].rc) return fail("GPU %d: %s", p, res[p].err.c_str());
@@ -787,12 +812,14 @@ int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_
     return 0;
   }
   return eval_host_one(dev, kernel_id, real_bytes, digits, Ns, 0, Nt, (const char*)r_src, (const char*)n_src, (const char*)v_src, (const char*)r_trg,
-                       (char*)v_trg, true);
+                       (char*)v_trg, ctx0, true);
 }
 
 int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg,
-                            void* M, int64_t ldM) {
+                            void* M, int64_t ldM, const void* ctx, int64_t ctx_bytes) {
   if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  double ctx0;
+  if (decode_ctx(kernel_id, real_bytes, ctx, ctx_bytes, &ctx0)) return 1;
   const KernelInfo ki = kernel_info(kernel_id);
   int dev;
   if (current_device_ready(&dev)) return 1;
@@ -809,7 +836,7 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
   CU_TRY(cudaMemcpyAsync(d_rs.p, r_src, rb * Ns * 3, cudaMemcpyHostToDevice, st));
   if (ki.nd) CU_TRY(cudaMemcpyAsync(d_ns.p, n_src, rb * Ns * ki.nd, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg, rb * Nt * 3, cudaMemcpyHostToDevice, st));
-  if (kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_rs.p, d_ns.p, d_rt.p, d_M.p, cols, st)) return 1;
+  if (kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_rs.p, d_ns.p, d_rt.p, d_M.p, cols, ctx0, st)) return 1;
   CU_TRY(cudaMemcpy2DAsync(M, rb * ldM, d_M.p, rb * cols, rb * cols, rows, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   return 0;

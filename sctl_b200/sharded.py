@@ -26,8 +26,8 @@ def _meta(kernel):
     return k.kernel_id, k.SrcDim(), k.TrgDim(), k.NormalDim()
 
 
-def _cuda_compute(kernel_id, r_src, n_src, v_src, r_trg, v_trg, digits):
-    eval_device(kernel_id, r_src, n_src, v_src, r_trg, v_trg, digits=digits)
+def _cuda_compute(kernel_id, r_src, n_src, v_src, r_trg, v_trg, digits, ctx=None):
+    eval_device(kernel_id, r_src, n_src, v_src, r_trg, v_trg, digits=digits, ctx=ctx)
 
 
 class ShardedEval:
@@ -38,13 +38,13 @@ class ShardedEval:
     ``v_trg_local`` when given).  ``gather`` assembles the full result on every rank.
     """
 
-    def __init__(self, kernel, Ns, Nt, dtype=torch.float64, device=None, group=None, compute=None):
+    def __init__(self, kernel, Ns, Nt, dtype=torch.float64, device=None, group=None, compute=None, ctx=None):
         self.kernel_id, self.k0, self.k1, self.nd = _meta(kernel)
         self.Ns, self.Nt, self.dtype, self.group = int(Ns), int(Nt), dtype, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu"))
-        self.compute = compute or _cuda_compute
+        self.compute = compute or (lambda *a: _cuda_compute(*a, ctx=ctx))
         self.s0, self.s1 = block_range(self.Ns, self.rank, self.world)
         self.t0, self.t1 = block_range(self.Nt, self.rank, self.world)
         new = lambda n: torch.empty(n, dtype=dtype, device=self.device)

@@ -37,7 +37,7 @@ def main():
             err = float(np.abs(got - want).max() / np.abs(want).max())
             assert err <= 1e-12, (kernel, err)
             single = torch.zeros(Nt * k1, dtype=torch.float64, device=dev)
-            sb.eval_device(kernel, td(R), td(N), td(V), td(T), single)
+            sb.eval_device(sb.KERNELS[kernel], td(R), td(N), td(V), td(T), single)
             torch.cuda.synchronize()
             assert float(np.abs(single.cpu().numpy() - full).max() / np.abs(full).max()) <= 1e-13
     dist.barrier()

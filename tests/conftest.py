@@ -61,4 +61,8 @@ def sb():
     sctl_b200.load_library()
     if sctl_b200.device_count() < 1:
         pytest.fail("gpu test selected but no CUDA device is visible (the product has no CPU fallback)")
+    import cases
+    for name, ctx in cases.CTX.items():  # the Helmholtz kernels carry their wavenumber as the kernel context
+        if ctx is not None:
+            sctl_b200.KERNELS[name].SetCtxPtr(ctx)
     return sctl_b200

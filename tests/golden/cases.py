@@ -7,7 +7,10 @@ from sctl_b200 import synth
 KERNELS = {"Laplace3D_FxU": (1, 1, 0), "Laplace3D_DxU": (1, 1, 3), "Laplace3D_FxdU": (1, 3, 0), "Stokes3D_FxU": (3, 3, 0), "Stokes3D_DxU": (3, 3, 3),
            # beyond the north-star five
            "Stokes3D_FxT": (3, 9, 0), "Stokes3D_FSxU": (4, 3, 0), "Stokes3D_FxUP": (3, 4, 0), "Laplace3D_Fxd2U": (1, 9, 0), "Laplace3D_DxdU": (1, 3, 3),
-           "BiotSavart3D_FxU": (3, 3, 0), "BiotSavart3D_FxdU": (3, 9, 0)}
+           "BiotSavart3D_FxU": (3, 3, 0), "BiotSavart3D_FxdU": (3, 9, 0),
+           "Helmholtz3D_FxU": (2, 2, 0), "Helmholtz3D_DxU": (2, 2, 3), "Helmholtz3D_FxdU": (2, 6, 0), "HelmholtzDiff3D_FxdU": (2, 6, 0)}
+# kernel context (the Helmholtz wavenumber) used by every fixture; None for the kernels without one
+CTX = {k: (1.7 if "Helmholtz" in k else None) for k in KERNELS}  # == oracle.DEFAULT_HELMHOLTZ_CTX
 NORTH_STAR = ["Laplace3D_FxU", "Laplace3D_DxU", "Laplace3D_FxdU", "Stokes3D_FxU", "Stokes3D_DxU"]
 
 # (Ns, Nt, variant, digits): variants -- "cube": distinct sets; "self": targets == sources (r2 == 0 pairs);

@@ -24,10 +24,10 @@ def main():
         for dtype in (np.float64, np.float32):
             for Ns, Nt, variant, digits in cases.EVAL_CASES:
                 r_src, n_src, v_src, r_trg, v0 = cases.inputs(kernel, Ns, Nt, variant, dtype)
-                out[cases.key(kernel, dtype, Ns, Nt, variant, digits)] = ref.eval(kernel, r_src, n_src, v_src, r_trg, v_trg=v0, dtype=dtype, omp=True, digits=digits)
+                out[cases.key(kernel, dtype, Ns, Nt, variant, digits)] = ref.eval(kernel, r_src, n_src, v_src, r_trg, v_trg=v0, dtype=dtype, omp=True, digits=digits, ctx=cases.CTX[kernel] or 0.0)
             for Ns, Nt in cases.KMAT_CASES:
                 r_src, n_src, v_src, r_trg, _ = cases.inputs(kernel, Ns, Nt, "cube", dtype)
-                out[cases.kmat_key(kernel, dtype, Ns, Nt)] = ref.kernel_matrix(kernel, r_src, n_src, r_trg, dtype=dtype, omp=False)
+                out[cases.kmat_key(kernel, dtype, Ns, Nt)] = ref.kernel_matrix(kernel, r_src, n_src, r_trg, dtype=dtype, omp=False, ctx=cases.CTX[kernel] or 0.0)
     # approx_rsqrt<digits> samples (vec-test.hpp:431-465 style): x over 40 decades, plus masked lanes
     x = np.concatenate([10.0 ** np.linspace(-20, 20, 397), [0.0, 1.0, 4.0, 0.25]])
     out["rsqrt/x"] = x

@@ -18,7 +18,7 @@ def _subset_check(sb, cpu_oracle, kernel, N, dtype, nsub, tol):
     r_src, n_src, v_src, r_trg = synth.cube(N, N, k0, nd, dtype=dtype)
     d = [None if a is None else torch.from_numpy(a).cuda() for a in (r_src, n_src, v_src, r_trg)]
     d_v = torch.zeros(N * k1, dtype=tdt, device="cuda")
-    sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_v)
+    sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_v)
     torch.cuda.synchronize()
     v = d_v.cpu().numpy()
     assert np.all(np.isfinite(v))
@@ -85,7 +85,7 @@ def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
     pre = (synth.splitmix_u01(13, Nt * k1) - 0.5).astype(dtype)
     d = [None if a is None else torch.from_numpy(a).cuda() for a in (r_src, n_src, v_src, r_trg)]
     d_v = torch.from_numpy(pre).cuda()
-    sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_v)
+    sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_v)
     torch.cuda.synchronize()
     plan = sb.last_plan()
     assert plan["grid_y"] == 2 and plan["n_launches"] >= 3, plan  # pack + one launch per chunk, cluster of 2
@@ -96,7 +96,7 @@ def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
     assert rel_err(got[idx].reshape(-1), want) <= tol, (kernel, rel_err(got[idx].reshape(-1), want))
     # same inputs again: bit-identical (no atomics anywhere)
     d_w = torch.from_numpy(pre).cuda()
-    sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_w)
+    sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_w)
     torch.cuda.synchronize()
     assert torch.equal(d_v, d_w)
     sb.set_option("const_fp32", 0)

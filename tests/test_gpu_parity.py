@@ -191,7 +191,7 @@ def test_device_path_unaligned_views_and_streams(sb, cpu_oracle, dtype):
         st = torch.cuda.Stream()
         st.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(st):
-            sb.eval_device(kernel, d[0], d[1], d[2], d[3], d_v)
+            sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_v)
         st.synchronize()
         want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg, v_trg=pre, dtype=dtype)
         assert rel_err(d_v.cpu().numpy(), want) <= TOL[dtype]
@@ -200,7 +200,7 @@ def test_device_path_unaligned_views_and_streams(sb, cpu_oracle, dtype):
         Nsm, Ntm = 37, 53
         ld = Ntm * k1 + 3
         dM = torch.full((Nsm * k0, ld), -7.0, dtype=tdt, device="cuda")
-        sb.kernel_matrix_device(kernel, d[0][: Nsm * 3], None if d[1] is None else d[1][: Nsm * 3], d[3][: Ntm * 3], dM, ldM=ld)
+        sb.kernel_matrix_device(sb.KERNELS[kernel], d[0][: Nsm * 3], None if d[1] is None else d[1][: Nsm * 3], d[3][: Ntm * 3], dM, ldM=ld)
         torch.cuda.synchronize()
         Mh = dM.cpu().numpy()
         wantM = cpu_oracle.kernel_matrix(kernel, r_src[: Nsm * 3], None if n_src is None else n_src[: Nsm * 3], r_trg[: Ntm * 3], dtype=dtype)

@@ -57,7 +57,7 @@ def test_kernel_info_matches_oracle_and_python_mirror(sbm, port):
         assert abs(float(K.uKerScaleFactor(np.float32)) - d["scale32"]) < 1e-7
     assert sbm.kernel_info(3)["f_alg"] == 29  # Stokes3D_FxU algorithmic flop per pair
     with pytest.raises(sbm.SctlCudaError):
-        sbm.kernel_info(12)
+        sbm.kernel_info(16)
 
 
 def test_planner_fills_waves(sbm):
