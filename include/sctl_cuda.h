@@ -123,16 +123,45 @@ int sctl_cuda_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
 /* Launch geometry the last device-level Eval of the calling thread used (any pointer may be NULL). */
 int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes, int* ctas_per_sm, int* n_launches, double* wave_eff);
 
+/* ---- Device-resident direct evaluator -------------------------------------------------
+ * The ParticleFMM::EvalDirect analogue (fmm-wrapper.txx:551-623; driven once per GMRES iteration by
+ * BoundaryIntegralOp::ComputeFarField, boundary_integral.txx:1286-1305): source and target coordinates are uploaded
+ * once and stay in HBM, an apply ships only the density in and the potential out.  Sources and targets are
+ * addressed by small non-negative slot numbers chosen by the caller (the C++ mirror maps ParticleFMM's names to
+ * them).  With n_gpus > 1 the targets are sharded by contiguous block over GPUs 0..n_gpus-1 (the rule of
+ * fmm-wrapper.txx:568) and every GPU holds all sources; no reduction, so results do not depend on n_gpus.
+ *   set_src_coord    ParticleFMM::SetSrcCoord(name, X, Xn)   (fmm-wrapper.hpp:166)  normal_dim 0 or 3
+ *   set_src_density  ParticleFMM::SetSrcDensity(name, F)     (:174)  n_reals = Ns * K0 of the kernels that use it
+ *   set_trg_coord    ParticleFMM::SetTrgCoord(name, X)       (:182)
+ *   set_kernel_s2t   ParticleFMM::SetKernelS2T(src, trg, k)  (:143)  kernel_id < 0 removes the interaction
+ *   eval             ParticleFMM::EvalDirect(U, trg)         (:198)  U[Nt*K1] is OVERWRITTEN with the sum over every
+ *                    source slot that has a kernel into `trg` (fmm-wrapper.txx:562-563,598-619); digits as in Eval.
+ * All pointers are host pointers; nothing is retained after return.  A session serialises its own calls. */
+typedef struct sctl_cuda_direct_s* sctl_cuda_direct_t;
+int sctl_cuda_direct_create(int real_bytes, int n_gpus /* 0 or 1: the first GPU */, sctl_cuda_direct_t* out);
+int sctl_cuda_direct_destroy(sctl_cuda_direct_t h);
+int sctl_cuda_direct_set_src_coord(sctl_cuda_direct_t h, int src, int64_t Ns, const void* X, const void* Xn, int normal_dim);
+int sctl_cuda_direct_set_src_density(sctl_cuda_direct_t h, int src, int64_t n_reals, const void* F);
+int sctl_cuda_direct_set_trg_coord(sctl_cuda_direct_t h, int trg, int64_t Nt, const void* X);
+int sctl_cuda_direct_set_kernel_s2t(sctl_cuda_direct_t h, int src, int trg, int kernel_id, const void* ctx, int64_t ctx_bytes);
+int sctl_cuda_direct_eval(sctl_cuda_direct_t h, int trg, int digits, void* U, int64_t n_reals);
+
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
- *   "const_min_targets" (default 2^18): at or above, sources are streamed through the constant bank in chunks
+ *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks
  *                       (FP64 only unless "const_fp32" is set to 1);
  *   "wide_min_targets"  (default 2^16): at or above (FP64), 4 targets per thread, one CTA per SM;
  *   "few_max_targets"   (default 2048): at or below, the warps of a CTA share 32 targets and split the sources.
+ *   "const_banks"       (default 2): slices of the constant buffer in flight on the constant-bank path; chunk i
+ *                       streams through slice i % banks on its own stream so consecutive launches overlap (1..4);
+ *   "const_ctas_per_sm" / "const_ctas_per_sm_overlap" (defaults 6 / 1): CTAs per SM a launch should have before its
+ *                       chunk is split across a thread-block cluster (one launch at a time / overlapping launches);
  *   "probe_min_pairs"   (default 2e9): at or above Ns*Nt, Eval first checks (O(Ns+Nt), on the device) whether any source
  *                       and target (nearly) coincide and lets the pair kernels drop the r^2 == 0 mask when none do;
  *                       <= 0 disables the check.  Results are bit-identical either way.
  * Results agree to rounding whichever path runs; the knobs exist for tuning and for tests. */
 int sctl_cuda_set_option(const char* name, int64_t value);
+/* Back to the built-in defaults. */
+int sctl_cuda_reset_options(void);
 
 /* The grid planner, exposed for host-side tests (no GPU needed): for Nt targets in blocks of `tpb`, Ns sources
  * and `slots` resident CTAs (SMs x CTAs/SM) returns the number of source chunks, their length and the fraction

@@ -54,6 +54,13 @@ def load_library():
     L.sctl_cuda_last_plan.argtypes = [ip, ip, ip, ip, ip, ip, dp]
     L.sctl_cuda_fma_peak.argtypes = [i, C.c_double, dp]
     L.sctl_cuda_set_option.argtypes = [C.c_char_p, i64]
+    L.sctl_cuda_direct_create.argtypes = [i, i, C.POINTER(vp)]
+    L.sctl_cuda_direct_destroy.argtypes = [vp]
+    L.sctl_cuda_direct_set_src_coord.argtypes = [vp, i, i64, vp, vp, i]
+    L.sctl_cuda_direct_set_src_density.argtypes = [vp, i, i64, vp]
+    L.sctl_cuda_direct_set_trg_coord.argtypes = [vp, i, i64, vp]
+    L.sctl_cuda_direct_set_kernel_s2t.argtypes = [vp, i, i, i, vp, i64]
+    L.sctl_cuda_direct_eval.argtypes = [vp, i, i, vp, i64]
     L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
     _lib = L
     return L
@@ -111,8 +118,13 @@ def last_plan():
 
 
 def set_option(name, value):
-    """sctl_cuda_set_option: 'const_min_targets', 'wide_min_targets', 'few_max_targets' (Eval path selection)."""
+    """sctl_cuda_set_option: Eval path selection and tuning knobs (include/sctl_cuda.h lists them)."""
     _check(load_library().sctl_cuda_set_option(name.encode(), int(value)))
+
+
+def reset_options():
+    """sctl_cuda_reset_options: every tuning knob back to its built-in default."""
+    _check(load_library().sctl_cuda_reset_options())
 
 
 def plan_eval(Ns, Nt, tpb, slots, min_chunk, max_split):
@@ -327,3 +339,105 @@ Helmholtz3D_DxU = GenericKernel("Helmholtz3D_DxU")
 Helmholtz3D_FxdU = GenericKernel("Helmholtz3D_FxdU")
 HelmholtzDiff3D_FxdU = GenericKernel("HelmholtzDiff3D_FxdU")
 KERNELS = {name: GenericKernel(name) for name in KERNEL_IDS}
+
+
+class ParticleDirect:
+    """Device-resident direct evaluator: the ``ParticleFMM::EvalDirect`` analogue (fmm-wrapper.hpp:35-200,
+    fmm-wrapper.txx:551-623) over ``sctl_cuda_direct_*``.  Same method names and argument meaning as ``ParticleFMM``
+    for the subset EvalDirect uses; coordinates are uploaded once and stay in HBM, an apply ships only the density in
+    and the potential out.  ``n_gpus > 1`` shards the targets over GPUs 0..n_gpus-1 (results do not depend on it)."""
+
+    def __init__(self, dtype=np.float64, n_gpus=1):
+        self._dtype = np.dtype(dtype).type
+        self._h = C.c_void_p()
+        self._src, self._trg = {}, {}
+        self._digits = 10  # ParticleFMM's default accuracy (fmm-wrapper.txx:205)
+        _check(load_library().sctl_cuda_direct_create(np.dtype(dtype).itemsize, int(n_gpus), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            load_library().sctl_cuda_direct_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def SetAccuracy(self, digits):
+        self._digits = int(digits)
+
+    def AddSrc(self, name, ker_s2m=None, ker_s2l=None):
+        """``AddSrc(name, ker_s2m, ker_s2l)`` (fmm-wrapper.hpp:124); the FMM kernels are irrelevant to direct evaluation."""
+        if name in self._src:
+            raise SctlCudaError("Source name already exists.")
+        self._src[name] = max(self._src.values(), default=-1) + 1
+
+    def AddTrg(self, name, ker_m2t=None, ker_l2t=None):
+        if name in self._trg:
+            raise SctlCudaError("Target name already exists.")
+        self._trg[name] = max(self._trg.values(), default=-1) + 1
+
+    def _slot(self, table, name, what):
+        if name not in table:
+            raise SctlCudaError("%s name does not exist." % what)  # SCTL_ASSERT_MSG, fmm-wrapper.txx:555,574
+        return table[name]
+
+    def SetKernelS2T(self, src_name, trg_name, ker_s2t):
+        k = ker_s2t if isinstance(ker_s2t, GenericKernel) else GenericKernel(ker_s2t)
+        ctx, nb = k._ctx_arg(self._dtype)
+        _check(load_library().sctl_cuda_direct_set_kernel_s2t(self._h, self._slot(self._src, src_name, "Source"), self._slot(self._trg, trg_name, "Target"),
+                                                              k.kernel_id, _np_ptr(ctx), nb))
+
+    def DeleteSrc(self, name):
+        s = self._slot(self._src, name, "Source")
+        for t in self._trg.values():
+            _check(load_library().sctl_cuda_direct_set_kernel_s2t(self._h, s, t, -1, None, 0))
+        _check(load_library().sctl_cuda_direct_set_src_coord(self._h, s, 0, None, None, 0))
+        del self._src[name]
+
+    def DeleteTrg(self, name):
+        t = self._slot(self._trg, name, "Target")
+        for s in self._src.values():
+            _check(load_library().sctl_cuda_direct_set_kernel_s2t(self._h, s, t, -1, None, 0))
+        _check(load_library().sctl_cuda_direct_set_trg_coord(self._h, t, 0, None))
+        del self._trg[name]
+
+    def SetSrcCoord(self, name, src_coord, src_normal=None):
+        X = np.ascontiguousarray(src_coord, dtype=self._dtype).reshape(-1)
+        Ns = X.size // 3
+        if X.size != Ns * 3:
+            raise SctlCudaError("src_coord.Dim() == Ns*DIM violated")
+        Xn, nd = None, 0
+        if src_normal is not None and np.asarray(src_normal).size:
+            Xn = np.ascontiguousarray(src_normal, dtype=self._dtype).reshape(-1)
+            nd = 3
+            if Xn.size != Ns * 3:
+                raise SctlCudaError("src_normal.Dim() == Ns*DIM violated")
+        _check(load_library().sctl_cuda_direct_set_src_coord(self._h, self._slot(self._src, name, "Source"), Ns, _np_ptr(X), _np_ptr(Xn), nd))
+
+    def SetSrcDensity(self, name, src_density):
+        F = np.ascontiguousarray(src_density, dtype=self._dtype).reshape(-1)
+        _check(load_library().sctl_cuda_direct_set_src_density(self._h, self._slot(self._src, name, "Source"), F.size, _np_ptr(F)))
+
+    def SetTrgCoord(self, name, trg_coord):
+        X = np.ascontiguousarray(trg_coord, dtype=self._dtype).reshape(-1)
+        Nt = X.size // 3
+        if X.size != Nt * 3:
+            raise SctlCudaError("trg_coord.Dim() == Nt*DIM violated")
+        self._nt = getattr(self, "_nt", {})
+        self._nt[name] = Nt
+        _check(load_library().sctl_cuda_direct_set_trg_coord(self._h, self._slot(self._trg, name, "Target"), Nt, _np_ptr(X)))
+
+    def EvalDirect(self, U, trg_name, trg_dim):
+        """``EvalDirect(U, trg_name)`` (fmm-wrapper.txx:551-623): U is resized if needed and OVERWRITTEN.  ``trg_dim`` is
+        the target dof of the kernels into ``trg_name`` (ParticleFMM reads it from the kernel given to AddTrg)."""
+        t = self._slot(self._trg, trg_name, "Target")
+        n = self._nt[trg_name] * int(trg_dim)
+        if U is None or not isinstance(U, np.ndarray) or U.size != n or U.dtype != self._dtype or not U.flags.c_contiguous:
+            U = np.zeros(n, dtype=self._dtype)
+        _check(load_library().sctl_cuda_direct_eval(self._h, t, self._digits, _np_ptr(U.reshape(-1)), n))
+        return U
+
+    Eval = EvalDirect

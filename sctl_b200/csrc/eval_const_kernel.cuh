@@ -36,12 +36,22 @@ template <class Real> struct ConstEvalArgs {
   int64_t Nt;
   int n_rec;          // records in the constant bank for this launch
   int sub_len;        // records per cluster rank (grid.y slice)
+  int bank_off;       // first Real of this launch's bank inside c_src_pack (multi-bank streaming, see below)
   int allow_unmasked; // this call ran the coincidence probe: c_eval_must_mask is meaningful
   Real scale;
   Real ctx0;          // kernel context by value (Helmholtz wavenumber)
 };
 
 template <class Real, int KID> constexpr int const_chunk_records() { return CONST_PACK_BYTES / (RecTraits<Real, KID>::REC * (int)sizeof(Real)); }
+
+// Multi-bank streaming: the buffer is cut into `banks` equal slices and chunk i goes through slice i % banks on its
+// own stream, so the launch for chunk i+1 is already queued (its slice filled) while chunk i runs and its CTAs take
+// over the SMs as chunk i's last wave drains -- no idle tail and no wave quantisation per launch.  Launches that
+// share a slice are ordered by their stream; launches of different slices accumulate into different buffers.
+constexpr int CONST_MAX_BANKS = 4;
+template <class Real, int KID> inline int const_bank_records(int banks) {
+  return (CONST_PACK_BYTES / banks / 16 * 16) / (RecTraits<Real, KID>::REC * (int)sizeof(Real));
+}
 
 // NT is the LARGEST block the kernel may be launched with; the host picks blockDim.x = 32 * (warps per CTA) <= NT so
 // that every SM gets the same number of warps (see launch_eval_const in sctl_cuda.cu).
@@ -62,7 +72,7 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
     for (int k = 0; k < K1; k++) acc[j][k] = 0;
   }
   // Loop bounds are kept in a form ptxas recognises as warp-uniform, otherwise it falls back to vector LDC.
-  const Real* src = reinterpret_cast<const Real*>(c_src_pack) + (int)blockIdx.y * a.sub_len * REC;
+  const Real* src = reinterpret_cast<const Real*>(c_src_pack) + a.bank_off + (int)blockIdx.y * a.sub_len * REC;
   const int n = (blockIdx.y + 1 == gridDim.y) ? a.n_rec - (int)blockIdx.y * a.sub_len : a.sub_len;
   if (a.allow_unmasked && c_eval_must_mask[0] == 0) {
 #pragma unroll U

@@ -71,6 +71,9 @@ struct DeviceInfo {
   // enqueued under this mutex and chained on the GPU through `const_done`, whatever stream they run on.
   std::mutex const_mu;
   cudaEvent_t const_done = nullptr;
+  cudaEvent_t const_fork = nullptr;
+  cudaStream_t bank_stream[CONST_MAX_BANKS] = {};  // [0] unused: bank 0 runs on the caller's stream
+  cudaEvent_t bank_done[CONST_MAX_BANKS] = {};
 };
 
 struct NcclApi {
@@ -89,9 +92,14 @@ struct Options {
   //   Nt <= few_max_targets   : shared-memory ring, all warps of a CTA share 32 targets and split the sources
   //   Nt >= wide_min_targets  : shared-memory ring, 4 targets per thread, one CTA per SM
   //   otherwise               : shared-memory ring, 2 targets per thread, two CTAs per SM
-  int64_t const_min_targets = 1 << 18;
+  int64_t const_min_targets = 1 << 15;
   int64_t few_max_targets = 2048;
   int64_t wide_min_targets = 1 << 16;
+  // Constant-bank path: slices of the buffer in flight (1 = one launch at a time), and the CTAs per SM a launch should
+  // have before its chunk is split across a cluster (stand-alone launches / overlapping launches).
+  int64_t const_banks = 2;
+  int64_t const_ctas_per_sm = 6;
+  int64_t const_ctas_per_sm_overlap = 1;
   int64_t const_fp32 = 0;  // FP32 gains nothing from the constant-bank path (rates in profiles/): off by default
   // Above this many pairs Eval first runs the O(Ns+Nt) coincidence probe (coincidence.cuh) and lets the pair kernels
   // drop the r2 == 0 mask when no source/target pair can need it.  <= 0 disables the probe (always mask).
@@ -262,15 +270,24 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   using Tn = Tune<Real>;
   constexpr int T = Tn::CONST_T, NT = Tn::CONST_NT;
   constexpr int REC = RecTraits<Real, KID>::REC;
-  constexpr int CH = const_chunk_records<Real, KID>();
+  constexpr int K1 = KerTraits<KID>::K1;
   auto kern = eval_pairs_const_kernel<Real, KID, T, NT, RSQ, Tn::CONST_U, Tn::CONST_MINB>;
   const int64_t n_tb = (Nt + NT * T - 1) / (NT * T);
   if (n_tb > 2147483647LL) return fail("too many target blocks");
+  DeviceInfo& di = g.dev[dev];
+  // Banks: chunk i streams through slice i % banks of the constant buffer on its own stream (eval_const_kernel.cuh).
+  int banks = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.const_banks, CONST_MAX_BANKS));
+  const int CH = const_bank_records<Real, KID>(banks);
+  if ((Ns + CH - 1) / CH < 2 * banks) banks = 1;  // too few chunks to pipeline
+  const int CHB = const_bank_records<Real, KID>(banks);
+  const int bank_stride = (CONST_PACK_BYTES / banks / 16 * 16) / (int)sizeof(Real);
+  // Cluster split of a chunk along grid.y when target blocks alone cannot fill the SMs.  With one bank every launch
+  // stands alone and wants several CTAs per SM; with overlapping launches one CTA slot's worth per SM is enough.
+  const int64_t want_ctas = (banks > 1 ? g.opt.const_ctas_per_sm_overlap : g.opt.const_ctas_per_sm) * (int64_t)di.sms;
   int cl = 1;
-  while (cl < 8 && n_tb * cl < 6 * (int64_t)g.dev[dev].sms) cl *= 2;  // >= 6 CTAs per SM keeps the SMs balanced
-  ConstEvalArgs<Real> a;
+  while (cl < 8 && n_tb * cl < want_ctas) cl *= 2;
+  ConstEvalArgs<Real> a = {};
   a.r_trg = r_trg;
-  a.v_trg = v_trg;
   a.Nt = Nt;
   a.allow_unmasked = must_mask != nullptr;
   a.ctx0 = ctx0;
@@ -278,7 +295,6 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_tb, (unsigned)cl);
   cfg.blockDim = dim3(NT);
-  cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
@@ -287,25 +303,58 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   cfg.attrs = attr;
   cfg.numAttrs = cl > 1 ? 1 : 0;
 
-  DeviceInfo& di = g.dev[dev];
   std::lock_guard<std::mutex> lk(di.const_mu);
-  if (!di.const_done) CU_TRY(cudaEventCreateWithFlags(&di.const_done, cudaEventDisableTiming));
-  else CU_TRY(cudaStreamWaitEvent(stream, di.const_done, 0));  // the previous user of the constant bank, on any stream
+  if (!di.const_done) {
+    CU_TRY(cudaEventCreateWithFlags(&di.const_done, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&di.const_fork, cudaEventDisableTiming));
+    for (int b = 1; b < CONST_MAX_BANKS; b++) {
+      CU_TRY(cudaStreamCreateWithFlags(&di.bank_stream[b], cudaStreamNonBlocking));
+      CU_TRY(cudaEventCreateWithFlags(&di.bank_done[b], cudaEventDisableTiming));
+    }
+  } else {
+    CU_TRY(cudaStreamWaitEvent(stream, di.const_done, 0));  // the previous user of the constant bank, on any stream
+  }
   if (must_mask) CU_TRY(cudaMemcpyToSymbolAsync(c_eval_must_mask, must_mask, sizeof(int), 0, cudaMemcpyDeviceToDevice, stream));
+  // banks 1.. accumulate into their own zeroed buffers (launches of different banks overlap and must not race on v_trg)
+  Real* alt = nullptr;
+  const size_t nv = (size_t)Nt * K1;
+  if (banks > 1) {
+    CU_TRY(cudaMallocAsync((void**)&alt, sizeof(Real) * nv * (banks - 1), stream));
+    CU_TRY(cudaMemsetAsync(alt, 0, sizeof(Real) * nv * (banks - 1), stream));
+    CU_TRY(cudaEventRecord(di.const_fork, stream));
+    for (int b = 1; b < banks; b++) CU_TRY(cudaStreamWaitEvent(di.bank_stream[b], di.const_fork, 0));
+  }
   int launches = 0;
-  for (int64_t s0 = 0; s0 < Ns; s0 += CH) {
-    const int n = (int)std::min<int64_t>(CH, Ns - s0);
-    CU_TRY(cudaMemcpyToSymbolAsync(c_src_pack, pack + s0 * REC, sizeof(Real) * (size_t)n * REC, 0, cudaMemcpyDeviceToDevice, stream));
+  int64_t i = 0;
+  for (int64_t s0 = 0; s0 < Ns; s0 += CHB, i++) {
+    const int b = (int)(i % banks);
+    cudaStream_t st = b ? di.bank_stream[b] : stream;
+    const int n = (int)std::min<int64_t>(CHB, Ns - s0);
+    CU_TRY(cudaMemcpyToSymbolAsync(c_src_pack, pack + s0 * REC, sizeof(Real) * (size_t)n * REC, sizeof(Real) * (size_t)b * bank_stride, cudaMemcpyDeviceToDevice, st));
+    a.v_trg = b ? alt + (size_t)(b - 1) * nv : v_trg;
     a.n_rec = n;
     a.sub_len = (n + cl - 1) / cl;
+    a.bank_off = b * bank_stride;
+    cfg.stream = st;
     CU_TRY(cudaLaunchKernelEx(&cfg, kern, a));
+    launches++;
+  }
+  if (banks > 1) {
+    for (int b = 1; b < banks; b++) {
+      CU_TRY(cudaEventRecord(di.bank_done[b], di.bank_stream[b]));
+      CU_TRY(cudaStreamWaitEvent(stream, di.bank_done[b], 0));
+    }
+    const int blocks = (int)std::min<int64_t>(((int64_t)nv + 255) / 256, 4096);
+    reduce_partials_kernel<Real><<<blocks, 256, 0, stream>>>((int64_t)nv, banks - 1, alt, (Real)1, v_trg);  // bank order: deterministic
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaFreeAsync(alt, stream));
     launches++;
   }
   CU_TRY(cudaEventRecord(di.const_done, stream));
   tl.grid_x = (int)n_tb;
   tl.grid_y = cl;
   tl.threads = NT;
-  tl.smem = (int)(sizeof(Real) * T * KerTraits<KID>::K1 * NT);
+  tl.smem = (int)(sizeof(Real) * T * K1 * NT);
   tl.ctas_per_sm = 0;
   tl.n_launches = launches;
   tl.wave_eff = 0;
@@ -360,7 +409,11 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
 
 template <class Real, int KID>
 int eval_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, Real ctx0, cudaStream_t stream) {
-  switch (rsq_mode_for_digits<Real>(digits)) {
+  int mode = rsq_mode_for_digits<Real>(digits);
+  // Helmholtz kernels feed r = r2 * rinv into sin/cos and cancel leading terms (HelmholtzDiff): the 2^-22 seed alone
+  // leaves FP32 results further from the reference than its own AVX-512 recipe (seed + 1 Newton step at digits 5-8)
+  if (KerNeedsCtx<KID>::value && sizeof(Real) == 4 && mode == RSQ_SEED && (digits < 0 || digits >= 5)) mode = RSQ_NEWTON;
+  switch (mode) {
     case RSQ_SEED: return eval_device_t<Real, KID, RSQ_SEED>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
     case RSQ_NEWTON: return eval_device_t<Real, KID, RSQ_NEWTON>(dev, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx0, stream);
     default:
@@ -668,6 +721,8 @@ constexpr double MULTI_GPU_MIN_PAIRS = 1.0e9;
 
 }  // namespace
 
+#include "direct_session.inc"
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -888,8 +943,17 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "few_max_targets")) g.opt.few_max_targets = value;
   else if (!strcmp(name, "wide_min_targets")) g.opt.wide_min_targets = value;
   else if (!strcmp(name, "const_fp32")) g.opt.const_fp32 = value;
+  else if (!strcmp(name, "const_banks")) g.opt.const_banks = value;
+  else if (!strcmp(name, "const_ctas_per_sm")) g.opt.const_ctas_per_sm = value;
+  else if (!strcmp(name, "const_ctas_per_sm_overlap")) g.opt.const_ctas_per_sm_overlap = value;
   else if (!strcmp(name, "probe_min_pairs")) g.opt.probe_min_pairs = value;
   else return fail("unknown option '%s'", name);
+  return 0;
+}
+
+int sctl_cuda_reset_options() {
+  std::lock_guard<std::mutex> lk(g.mu);
+  g.opt = Options();
   return 0;
 }
 

@@ -38,6 +38,15 @@ def test_reference_particle_fmm_through_the_dropin(sb):
     assert m and float(m.group(1)) < 1e-12, r.stdout[-2000:]
 
 
+def test_particle_direct_against_reference_particle_fmm(sb):
+    """sctl_cuda::ParticleDirect (include/sctl_cuda/particle_direct.hpp, device-resident coordinates) against the
+    reference's own ParticleFMM<Real,3>::EvalDirect running on the CPU, same call sequence: two source types into one
+    target set, a second target set, new densities with fixed coordinates (the GMRES pattern), moved targets,
+    DeleteSrc, Laplace potential at the sources themselves and gradient; FP64 1e-12, FP32 1e-5."""
+    r = _run("test_particle_direct")
+    assert r.returncode == 0 and "PASS (0 check(s) failed)" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_config5_boundary_integral_op_through_the_dropin(sb, tmp_path):
     """BASELINE config 5: the reference's unmodified BoundaryIntegralOp<double,Laplace3D_FxU>::ComputePotential on the
     synthetic torus (tests/cpp/bio_torus.cpp).  The CPU build of the same driver is the checker at 32768 nodes; the

@@ -69,38 +69,48 @@ def test_config4_kernels_fp32_fp64_large(sb, cpu_oracle, kernel):
     assert e_gpu <= max(1e-5, 2 * e_cpu), (kernel, e_gpu, e_cpu)
 
 
+# (const_banks, const_ctas_per_sm_overlap) -> expected cluster size (grid.y) at 513 target blocks on 148 SMs
+CONST_CONFIGS = [((1, 1), 2),   # one launch at a time: chunk split over a 2-CTA cluster (DSMEM reduction)
+                 ((2, 1), 1),   # default: two bank slices in flight on two streams, no cluster
+                 ((4, 8), 4)]   # four slices in flight and 4-CTA clusters
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("kernel", list(cases.KERNELS))
 def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
-    """Large Nt (>= 2^18) takes the chunk-streaming path (sources through the constant bank into uniform registers, one launch
-    per chunk, 2-CTA clusters at this size): several chunks, ragged last chunk, pre-filled v_trg, every kernel."""
+    """The chunk-streaming path (sources through the constant bank into uniform registers, one launch per chunk) in its
+    three shapes: single bank + cluster split, overlapping launches over 2 bank slices (the default), 4 slices + clusters.
+    Several chunks per slice, ragged last chunk, pre-filled v_trg, every kernel; run-to-run bit-identical."""
     import torch
     from sctl_b200 import synth
     k0, k1, nd = cases.KERNELS[kernel]
-    Nt, Ns = (1 << 18) + 77, 4500
-    tdt = torch.float64 if dtype == np.float64 else torch.float32
-    sb.set_option("const_min_targets", 1 << 18)
-    sb.set_option("const_fp32", 1)  # the FP32 instantiations exist and must be right even though FP64 alone uses them by default
+    Nt, Ns = (1 << 18) + 77, 9000
     r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
     pre = (synth.splitmix_u01(13, Nt * k1) - 0.5).astype(dtype)
     d = [None if a is None else torch.from_numpy(a).cuda() for a in (r_src, n_src, v_src, r_trg)]
-    d_v = torch.from_numpy(pre).cuda()
-    sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_v)
-    torch.cuda.synchronize()
-    plan = sb.last_plan()
-    assert plan["grid_y"] == 2 and plan["n_launches"] >= 3, plan  # pack + one launch per chunk, cluster of 2
-    got = d_v.cpu().numpy().reshape(-1, k1)
     idx = np.concatenate([np.arange(300) * (Nt // 300), [Nt - 1, Nt - 2, 1 << 17]])
     want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg.reshape(-1, 3)[idx].reshape(-1), v_trg=pre.reshape(-1, k1)[idx].reshape(-1), dtype=dtype)
     tol = 1e-12 if dtype == np.float64 else 1e-5
-    assert rel_err(got[idx].reshape(-1), want) <= tol, (kernel, rel_err(got[idx].reshape(-1), want))
-    # same inputs again: bit-identical (no atomics anywhere)
-    d_w = torch.from_numpy(pre).cuda()
-    sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_w)
-    torch.cuda.synchronize()
-    assert torch.equal(d_v, d_w)
-    sb.set_option("const_fp32", 0)
-    sb.set_option("const_min_targets", 1 << 18)
+    try:
+        sb.set_option("const_min_targets", 1 << 18)
+        sb.set_option("const_fp32", 1)  # the FP32 instantiations exist and must be right even though FP64 alone uses them by default
+        for (banks, ov), grid_y in CONST_CONFIGS:
+            sb.set_option("const_banks", banks)
+            sb.set_option("const_ctas_per_sm_overlap", ov)
+            d_v = torch.from_numpy(pre).cuda()
+            sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_v)
+            torch.cuda.synchronize()
+            plan = sb.last_plan()
+            assert plan["grid_y"] == grid_y and plan["n_launches"] >= 3 * banks, (banks, ov, plan)
+            got = d_v.cpu().numpy().reshape(-1, k1)
+            assert rel_err(got[idx].reshape(-1), want) <= tol, (kernel, banks, ov, rel_err(got[idx].reshape(-1), want))
+            # same inputs again: bit-identical (no atomics anywhere; launches of different slices use different buffers)
+            d_w = torch.from_numpy(pre).cuda()
+            sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_w)
+            torch.cuda.synchronize()
+            assert torch.equal(d_v, d_w), (kernel, banks, ov)
+    finally:
+        sb.reset_options()
 
 
 def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
@@ -134,7 +144,7 @@ def test_constant_bank_path_concurrent_streams(sb, cpu_oracle):
         idx = np.arange(100) * (Nt // 100)
         want = cpu_oracle.eval("Stokes3D_FxU", r_src, None, v_src, r_trg.reshape(-1, 3)[idx].reshape(-1))
         assert rel_err(v.reshape(-1, 3)[idx].reshape(-1), want) <= 1e-12
-    sb.set_option("const_min_targets", 1 << 18)
+    sb.reset_options()
 
 
 def test_target_permutation_equivariance(sb):

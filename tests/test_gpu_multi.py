@@ -52,3 +52,27 @@ def test_torchrun_sharded_eval_two_ranks(sb):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29631", script],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SHARDED_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_particle_direct_two_gpus(sb, cpu_oracle):
+    """sctl_cuda_direct_* with the targets sharded over 2 GPUs reproduces the single-GPU session bit for bit (no
+    reduction between GPUs) and the CPU oracle; the C++ mirror's own test program runs with 2 GPUs as well."""
+    _need_gpus(sb, 2)
+    from sctl_b200 import synth
+    Ns, Nt = 7001, 9007
+    r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, 3, 3)
+    res = []
+    for n in (1, 2):
+        pd = sb.ParticleDirect(np.float64, n_gpus=n)
+        pd.AddSrc("S"); pd.AddTrg("T")
+        pd.SetKernelS2T("S", "T", sb.Stokes3D_DxU)
+        pd.SetSrcCoord("S", r_src, n_src); pd.SetTrgCoord("T", r_trg); pd.SetSrcDensity("S", v_src)
+        pd.SetAccuracy(-1)
+        res.append(pd.EvalDirect(None, "T", 3))
+        pd.close()
+    assert np.array_equal(res[0], res[1])
+    assert rel_err(res[1], cpu_oracle.eval("Stokes3D_DxU", r_src, n_src, v_src, r_trg)) <= 1e-12
+    exe = os.path.join(ROOT, "tests", "_bin", "test_particle_direct")
+    if os.path.exists(exe):
+        r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "PASS (0 check(s) failed)" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

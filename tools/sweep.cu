@@ -194,7 +194,7 @@ void run_const(Ctx& c, int n_sub = 1, int wpc = 0) {
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, NT, 0));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, kern));
-  ConstEvalArgs<Real> a;
+  ConstEvalArgs<Real> a = {};
   a.r_trg = (const Real*)c.r_trg;
   a.v_trg = (Real*)c.v_trg;
   a.Nt = c.Nt;
@@ -254,7 +254,7 @@ void run_const_breakdown(Ctx& c) {
   constexpr int REC = RecTraits<Real, KID>::REC;
   constexpr int CH = const_chunk_records<Real, KID>();
   auto kern = eval_pairs_const_kernel<Real, KID, T, NT, RSQ, U, MINB>;
-  ConstEvalArgs<Real> a;
+  ConstEvalArgs<Real> a = {};
   a.r_trg = (const Real*)c.r_trg;
   a.v_trg = (Real*)c.v_trg;
   a.Nt = c.Nt;
