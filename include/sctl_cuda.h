@@ -146,6 +146,32 @@ int sctl_cuda_direct_set_trg_coord(sctl_cuda_direct_t h, int trg, int64_t Nt, co
 int sctl_cuda_direct_set_kernel_s2t(sctl_cuda_direct_t h, int src, int trg, int kernel_id, const void* ctx, int64_t ctx_bytes);
 int sctl_cuda_direct_eval(sctl_cuda_direct_t h, int trg, int digits, void* U, int64_t n_reals);
 
+/* ---- Batched near-field blocks of BoundaryIntegralOp -------------------------------------
+ * One session = one block list: the near_blk_* work list of BoundaryIntegralOp (boundary_integral.txx:1009-1032).
+ * Block b couples ns[b] source nodes with nt[b] near targets through a row-major, target-major operator block
+ * K_b of (nt[b]*K1) x (ns[b]*K0) Reals at K + k_dsp[b] (:1183); its density is F + f_dsp[b]*K0, its result
+ * U + u_dsp[b]*K1, its far-field nodes start at far_dsp[b] in Xs/Xn/wts, its targets at u_dsp[b] in Xt.  In the
+ * reference's variables: f_dsp = elem_nds_dsp[elem], far_dsp = elem_nds_dsp_far[elem], ns = elem_nds_cnt[elem],
+ * u_dsp = near_elem_dsp[elem] + t0, nt = near_blk_cnt[blk], k_dsp = K_near_dsp[elem]*K0*K1 + t0*K1*ns*K0.
+ *   set_matrix       upload K_near as the CPU singular/near quadrature left it; it then stays in HBM
+ *   subtract_direct  "KNearSubtract" (:1165-1240) for the case without a density operator and without
+ *                    trg_normal_dot_prod: K_b[(t*K1+k1)][(s*K0+k0)] -= wts[s] * KernelMatrix[(s*K0+k0)][(t*K1+k1)],
+ *                    every block in one launch
+ *   apply            "EvalNear" (:1324-1340): U_b = K_b * F_b for every block in one launch (overwrites U; blocks
+ *                    without sources give zeros, :1327-1331); F and U are host arrays, only they cross PCIe
+ *   get_matrix       download K (tests)
+ * All tables are copied at create; all pointers are host pointers; nothing is retained after return. */
+typedef struct sctl_cuda_near_s* sctl_cuda_near_t;
+int sctl_cuda_near_create(int real_bytes, int k0, int k1, int64_t n_blk, const int64_t* f_dsp, const int64_t* far_dsp, const int64_t* ns,
+                          const int64_t* u_dsp, const int64_t* nt, const int64_t* k_dsp, sctl_cuda_near_t* out);
+int sctl_cuda_near_destroy(sctl_cuda_near_t h);
+int sctl_cuda_near_sizes(sctl_cuda_near_t h, int64_t* K_len, int64_t* nF, int64_t* nU, int64_t* n_far);
+int sctl_cuda_near_set_matrix(sctl_cuda_near_t h, const void* K, int64_t n_reals);
+int sctl_cuda_near_get_matrix(sctl_cuda_near_t h, void* K, int64_t n_reals);
+int sctl_cuda_near_subtract_direct(sctl_cuda_near_t h, int kernel_id, int digits, int64_t Ns, const void* Xs, const void* Xn, const void* wts,
+                                   int64_t Nt, const void* Xt, const void* ctx, int64_t ctx_bytes);
+int sctl_cuda_near_apply(sctl_cuda_near_t h, const void* F, int64_t nF, void* U, int64_t nU);
+
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
  *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks
  *                       (FP64 only unless "const_fp32" is set to 1);

@@ -1,0 +1,46 @@
+"""TEST INFRASTRUCTURE ONLY -- numpy restatement of BoundaryIntegralOp's near-field block phases.
+
+Follows the reference loops in include/sctl/boundary_integral.txx:
+  * near_subtract  "KNearSubtract" (:1165-1240), the branch without trg_normal_dot_prod and with an empty K_direct
+    (element lists whose FarFieldDensityOperatorTranspose is the identity): Mker = KernelMatrix(Xtrg_near_, X, Xn)
+    (:1196-1197), rows scaled by wts[s] (:1198-1205), K_near_[i][j] -= Mker[j][i] (:1219-1229);
+  * near_apply     "EvalNear" (:1324-1340): U_ = K_near_ * F_ per block; blocks without sources give zeros (:1327-1331).
+KernelMatrix itself comes from the oracle object passed in (the C port or the unmodified reference).
+Block table columns as in include/sctl_cuda.h (f_dsp, far_dsp, ns, u_dsp, nt, k_dsp)."""
+import numpy as np
+
+
+def near_subtract(orc, kernel, k0, k1, nd, tab, K, Xs, Xn, wts, Xt, dtype=np.float64):
+    f_dsp, far_dsp, ns, u_dsp, nt, k_dsp = tab
+    K = np.array(K, dtype=dtype).reshape(-1)
+    Xs, Xt = np.asarray(Xs, dtype=dtype).reshape(-1, 3), np.asarray(Xt, dtype=dtype).reshape(-1, 3)
+    Xn = None if Xn is None else np.asarray(Xn, dtype=dtype).reshape(-1, 3)
+    wts = np.asarray(wts, dtype=dtype).reshape(-1)
+    for b in range(len(ns)):
+        if ns[b] == 0 or nt[b] == 0:
+            continue
+        s = slice(far_dsp[b], far_dsp[b] + ns[b])
+        t = slice(u_dsp[b], u_dsp[b] + nt[b])
+        M = orc.kernel_matrix(kernel, Xs[s].reshape(-1), None if Xn is None else Xn[s].reshape(-1), Xt[t].reshape(-1), dtype=dtype)  # (ns*k0) x (nt*k1)
+        M = M * np.repeat(wts[s], k0)[:, None]
+        rows, cols = nt[b] * k1, ns[b] * k0
+        blk = K[k_dsp[b]:k_dsp[b] + rows * cols].reshape(rows, cols)
+        blk -= M.T.astype(dtype)
+    return K
+
+
+def near_apply(k0, k1, tab, K, F, nU, dtype=np.float64):
+    f_dsp, far_dsp, ns, u_dsp, nt, k_dsp = tab
+    K = np.asarray(K, dtype=dtype).reshape(-1)
+    F = np.asarray(F, dtype=dtype).reshape(-1)
+    U = np.zeros(nU, dtype=dtype)
+    for b in range(len(ns)):
+        rows, cols = nt[b] * k1, ns[b] * k0
+        if rows == 0:
+            continue
+        if cols == 0:
+            U[u_dsp[b] * k1:u_dsp[b] * k1 + rows] = 0
+            continue
+        blk = K[k_dsp[b]:k_dsp[b] + rows * cols].reshape(rows, cols)
+        U[u_dsp[b] * k1:u_dsp[b] * k1 + rows] = blk @ F[f_dsp[b] * k0:f_dsp[b] * k0 + cols]
+    return U

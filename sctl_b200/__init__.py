@@ -61,6 +61,14 @@ def load_library():
     L.sctl_cuda_direct_set_trg_coord.argtypes = [vp, i, i64, vp]
     L.sctl_cuda_direct_set_kernel_s2t.argtypes = [vp, i, i, i, vp, i64]
     L.sctl_cuda_direct_eval.argtypes = [vp, i, i, vp, i64]
+    p64 = C.POINTER(i64)
+    L.sctl_cuda_near_create.argtypes = [i, i, i, i64, p64, p64, p64, p64, p64, p64, C.POINTER(vp)]
+    L.sctl_cuda_near_destroy.argtypes = [vp]
+    L.sctl_cuda_near_sizes.argtypes = [vp, p64, p64, p64, p64]
+    L.sctl_cuda_near_set_matrix.argtypes = [vp, vp, i64]
+    L.sctl_cuda_near_get_matrix.argtypes = [vp, vp, i64]
+    L.sctl_cuda_near_subtract_direct.argtypes = [vp, i, i, i64, vp, vp, vp, i64, vp, vp, i64]
+    L.sctl_cuda_near_apply.argtypes = [vp, vp, i64, vp, i64]
     L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
     _lib = L
     return L
@@ -441,3 +449,58 @@ class ParticleDirect:
         return U
 
     Eval = EvalDirect
+
+
+class NearBlocks:
+    """Batched near-field blocks of ``BoundaryIntegralOp`` on the device (``sctl_cuda_near_*``): the "KNearSubtract"
+    setup phase (boundary_integral.txx:1165-1240) and the per-iteration "EvalNear" apply (:1324-1340) over one block
+    list, with the operator resident in HBM.  Table columns are per block, in the units of include/sctl_cuda.h."""
+
+    def __init__(self, kernel, f_dsp, far_dsp, ns, u_dsp, nt, k_dsp, dtype=np.float64):
+        self.kernel = kernel if isinstance(kernel, GenericKernel) else GenericKernel(kernel)
+        self._dtype = np.dtype(dtype).type
+        cols = [np.ascontiguousarray(c, dtype=np.int64).reshape(-1) for c in (f_dsp, far_dsp, ns, u_dsp, nt, k_dsp)]
+        n = cols[0].size
+        if any(c.size != n for c in cols):
+            raise SctlCudaError("block table columns differ in length")
+        self._h = C.c_void_p()
+        L = load_library()
+        p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        _check(L.sctl_cuda_near_create(np.dtype(dtype).itemsize, self.kernel.SrcDim(), self.kernel.TrgDim(), n, *[p64(c) for c in cols], C.byref(self._h)))
+        v = [C.c_int64() for _ in range(4)]
+        _check(L.sctl_cuda_near_sizes(self._h, *[C.byref(x) for x in v]))
+        self.K_len, self.nF, self.nU, self.n_far = [x.value for x in v]
+
+    def close(self):
+        if self._h:
+            load_library().sctl_cuda_near_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_matrix(self, K):
+        K = np.ascontiguousarray(K, dtype=self._dtype).reshape(-1)
+        _check(load_library().sctl_cuda_near_set_matrix(self._h, _np_ptr(K), K.size))
+
+    def get_matrix(self):
+        K = np.zeros(self.K_len, dtype=self._dtype)
+        _check(load_library().sctl_cuda_near_get_matrix(self._h, _np_ptr(K), K.size))
+        return K
+
+    def subtract_direct(self, Xs, Xn, wts, Xt, digits=-1):
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=self._dtype).reshape(-1)
+        Xs, Xn, wts, Xt = c(Xs), c(Xn), c(wts), c(Xt)
+        ctx, nb = self.kernel._ctx_arg(self._dtype)
+        _check(load_library().sctl_cuda_near_subtract_direct(self._h, self.kernel.kernel_id, int(digits), Xs.size // 3, _np_ptr(Xs), _np_ptr(Xn), _np_ptr(wts),
+                                                             Xt.size // 3, _np_ptr(Xt), _np_ptr(ctx), nb))
+
+    def apply(self, F, U=None):
+        F = np.ascontiguousarray(F, dtype=self._dtype).reshape(-1)
+        if U is None or U.size < self.nU or U.dtype != self._dtype or not U.flags.c_contiguous:
+            U = np.zeros(self.nU, dtype=self._dtype)
+        _check(load_library().sctl_cuda_near_apply(self._h, _np_ptr(F), F.size, _np_ptr(U.reshape(-1)), U.size))
+        return U

@@ -1,0 +1,109 @@
+// Batched near-field blocks of BoundaryIntegralOp on the device.
+//
+// Reference (paths relative to /root/reference/include/sctl/):
+//   setup  boundary_integral.txx:1165-1240 ("KNearSubtract"): for every near block, KernelMatrix of the element's
+//          far-field nodes against the block's near targets, rows scaled by the quadrature weights, transposed and
+//          subtracted from the precomputed target-major operator block K_near_;
+//   apply  boundary_integral.txx:1324-1340 ("EvalNear"): per block U_ = K_near_ * F_ (row-major GEMV).
+// The reference walks the block list with OpenMP and calls KernelMatrix / GEMM once per block (hundreds x hundreds
+// each); through a host-pointer drop-in that is one H2D + launch + D2H per block.  Here the whole list is ONE launch
+// per phase over a (block, row-chunk) work list, and the operator stays in HBM between applies.
+//
+// Layouts (all the reference's): block b has ns_b source nodes and nt_b targets; K_b is row-major
+// (nt_b*K1) x (ns_b*K0) at K + k_dsp[b]  (target-major, :1183); F_b = F + f_dsp[b]*K0; U_b = U + u_dsp[b]*K1.
+// Bounds: subtract is HBM read-modify-write of K (2 * sizeof(Real) * K0*K1 bytes per pair, ~25 flop per pair);
+// apply is an HBM read of K (sizeof(Real) bytes per 2 flop).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pair_math.cuh"
+
+namespace sctl_cuda {
+
+struct NearBlocks {
+  int64_t n_blk;
+  const int64_t* f_dsp;    // [n_blk] first source node of the block in F (and in the block's element)
+  const int64_t* far_dsp;  // [n_blk] first far-field node of the block in Xs / Xn / wts
+  const int64_t* ns;       // [n_blk] source nodes
+  const int64_t* u_dsp;    // [n_blk] first target of the block in Xt / U
+  const int64_t* nt;       // [n_blk] targets
+  const int64_t* k_dsp;    // [n_blk] offset of K_b in K (Reals)
+  // work list: item w covers rows/targets [item_t0[w], item_t0[w] + ROWS) of block item_blk[w]
+  int64_t n_items;
+  const int32_t* item_blk;
+  const int32_t* item_t0;
+};
+
+constexpr int NEAR_SUB_TRG = 8;    // targets per work item in the subtract kernel
+constexpr int NEAR_APPLY_ROWS = 8; // matrix rows per work item in the apply kernel (one warp per row)
+
+// K_b[(t*K1+k1)][(s*K0+k0)] -= wts[s] * scale * K_{k0,k1}(x_t - x_s, n_s)
+// One CTA per work item (NEAR_SUB_TRG targets of one block); threads stride over the block's sources, so for a fixed
+// row the CTA touches consecutive columns (coalesced read-modify-write).  The pair arithmetic is the KernelMatrix
+// twin PairMatrix<KID> (pair_math.cuh), scaled per entry like generic-kernel.txx:268,306, then by the weight.
+template <class Real, int KID, int RSQ>
+__global__ void __launch_bounds__(128) near_subtract_kernel(const NearBlocks nb, const Real* __restrict__ Xs, const Real* __restrict__ Xn, const Real* __restrict__ wts,
+                                                            const Real* __restrict__ Xt, Real* __restrict__ K, Real scale, Real ctx0) {
+  constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
+  __shared__ Real xt_s[NEAR_SUB_TRG][3];
+  for (int64_t w = blockIdx.x; w < nb.n_items; w += gridDim.x) {
+    const int b = nb.item_blk[w];
+    const int64_t t0 = nb.item_t0[w];
+    const int64_t ns = nb.ns[b], nt = nb.nt[b];
+    const int n_t = (int)min((int64_t)NEAR_SUB_TRG, nt - t0);
+    __syncthreads();
+    if (threadIdx.x < n_t * 3) xt_s[threadIdx.x / 3][threadIdx.x % 3] = Xt[(nb.u_dsp[b] + t0) * 3 + threadIdx.x];
+    __syncthreads();
+    const int64_t ld = ns * K0;
+    Real* Kb = K + nb.k_dsp[b] + t0 * K1 * ld;
+    for (int64_t s = threadIdx.x; s < ns; s += blockDim.x) {
+      const int64_t gs = nb.far_dsp[b] + s;
+      const Real xs[3] = {Xs[gs * 3 + 0], Xs[gs * 3 + 1], Xs[gs * 3 + 2]};
+      Real n[3] = {0, 0, 0};
+      if (ND) {
+        n[0] = Xn[gs * 3 + 0];
+        n[1] = Xn[gs * 3 + 1];
+        n[2] = Xn[gs * 3 + 2];
+      }
+      const Real ws = wts[gs];
+      for (int t = 0; t < n_t; t++) {
+        Real dx[3] = {xt_s[t][0] - xs[0], xt_s[t][1] - xs[1], xt_s[t][2] - xs[2]};
+        const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
+        const Real rinv = rsqrt_masked<RSQ>(r2);
+        Real u[K0 * K1];
+        if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u, dx, rinv, n, r2, ctx0);
+        else PairMatrix<KID, Real>::run(u, dx, rinv, n);
+#pragma unroll
+        for (int k1 = 0; k1 < K1; k1++)
+#pragma unroll
+          for (int k0 = 0; k0 < K0; k0++) {
+            Real* p = Kb + (int64_t)(t * K1 + k1) * ld + s * K0 + k0;
+            *p -= (u[k0 * K1 + k1] * scale) * ws;  // KernelMatrix entry (scaled), times the weight (:1203), subtracted (:1228)
+          }
+      }
+    }
+  }
+}
+
+// U_b[r] = sum_c K_b[r][c] * F_b[c]; one warp per row, lanes stride the columns, fixed shuffle tree (deterministic).
+// Blocks with no sources write zeros (boundary_integral.txx:1327-1331).
+template <class Real>
+__global__ void __launch_bounds__(32 * NEAR_APPLY_ROWS) near_apply_kernel(const NearBlocks nb, int K0, int K1, const Real* __restrict__ K, const Real* __restrict__ F, Real* __restrict__ U) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t w = blockIdx.x; w < nb.n_items; w += gridDim.x) {
+    const int b = nb.item_blk[w];
+    const int64_t r = (int64_t)nb.item_t0[w] + warp;  // row of the block's matrix
+    const int64_t rows = nb.nt[b] * K1, cols = nb.ns[b] * K0;
+    if (r >= rows) continue;
+    const Real* Kr = K + nb.k_dsp[b] + r * cols;
+    const Real* Fb = F + nb.f_dsp[b] * K0;
+    Real acc = 0;
+    for (int64_t c = lane; c < cols; c += 32) acc = fma(Kr[c], Fb[c], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) U[nb.u_dsp[b] * K1 + r] = acc;
+  }
+}
+
+}  // namespace sctl_cuda

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -20,6 +21,7 @@
 #include "eval_const_kernel.cuh"
 #include "eval_kernel.cuh"
 #include "kmat_kernel.cuh"
+#include "near_kernel.cuh"
 
 using namespace sctl_cuda;
 
@@ -722,6 +724,7 @@ constexpr double MULTI_GPU_MIN_PAIRS = 1.0e9;
 }  // namespace
 
 #include "direct_session.inc"
+#include "near_session.inc"
 
 // =================================================================================================
 // C ABI

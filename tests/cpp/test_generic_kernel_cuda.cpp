@@ -5,9 +5,13 @@
 #include <cmath>
 #include <cstdio>
 #include <string>
+#include <vector>
+#include <algorithm>
 
 #include "sctl_cuda/generic_kernel.hpp"
 #include "sctl_cuda/mini_containers.hpp"
+#include "sctl_cuda/near_blocks.hpp"
+#include "sctl_cuda/particle_direct.hpp"
 
 namespace test_utils {
 static int failures = 0;
@@ -152,12 +156,89 @@ template <class R> static void kernel_function_fixtures() {
   check(sctl_cuda::Stokes3D_DxU(), 3, 3, 3);
 }
 
+// particle_direct.hpp / near_blocks.hpp with the mini containers: the resident evaluator must reproduce Eval, the
+// batched near blocks must reproduce per-block KernelMatrix + GEMV (the same device arithmetic, so tight tolerances).
+template <class R> static void session_layers() {
+  const R tol = sizeof(R) == 8 ? (R)1e-13 : (R)2e-5;
+  const Long Ns = 700, Nt = 450;
+  Vector<R> Xs(Ns * 3), Xn(Ns * 3), F(Ns * 3), Xt(Nt * 3), W(Ns);
+  unsigned long long z = 88172645463325252ULL;
+  auto rnd = [&z]() { z ^= z << 13; z ^= z >> 7; z ^= z << 17; return (R)((z >> 11) * (1.0 / 9007199254740992.0)) - (R)0.5; };
+  for (Long i = 0; i < Ns * 3; i++) { Xs[i] = rnd(); Xn[i] = rnd(); F[i] = rnd(); }
+  for (Long i = 0; i < Nt * 3; i++) Xt[i] = rnd();
+  for (Long i = 0; i < Ns; i++) W[i] = (R)0.01 + (R)0.001 * rnd();
+  sctl_cuda::Stokes3D_DxU dl;
+  sctl_cuda::Stokes3D_FxU sl;
+  {
+    sctl_cuda::ParticleDirect<R> pd;
+    pd.SetAccuracy(-1);
+    pd.AddSrc("S", sl, sl);
+    pd.AddSrc("D", dl, dl);
+    pd.AddTrg("T", sl, sl);
+    pd.SetKernelS2T("S", "T", sl);
+    pd.SetKernelS2T("D", "T", dl);
+    pd.SetSrcCoord("S", Xs);
+    pd.SetSrcCoord("D", Xs, Xn);
+    pd.SetSrcDensity("S", F);
+    pd.SetSrcDensity("D", F);
+    pd.SetTrgCoord("T", Xt);
+    Vector<R> U, V, none;
+    pd.Eval(U, "T");
+    sl.template Eval<R, true>(V, Xt, Xs, none, F);
+    dl.template Eval<R, true>(V, Xt, Xs, Xn, F);
+    CHECK(U.Dim() == Nt * 3 && V.Dim() == Nt * 3);
+    R err = 0, mag = 0;
+    for (Long i = 0; i < U.Dim(); i++) { err = std::fmax(err, std::fabs(U[i] - V[i])); mag = std::fmax(mag, std::fabs(V[i])); }
+    CHECK(err <= tol * mag);
+  }
+  {  // two elements (300 and 400 nodes), near targets cut into blocks of 64
+    using LV = Vector<Long>;
+    LV elem_nds_cnt({300, 400}), elem_nds_dsp({0, 300}), near_elem_dsp({0, 200}), near_elem_cnt({200, 250}), K_near_dsp({0, 300 * 200});
+    std::vector<Long> be, bt, bc;
+    for (Long e = 0; e < 2; e++)
+      for (Long t0 = 0; t0 < near_elem_cnt[e]; t0 += 64) { be.push_back(e); bt.push_back(t0); bc.push_back(std::min<Long>(64, near_elem_cnt[e] - t0)); }
+    LV blk_e((Long)be.size()), blk_t((Long)be.size()), blk_c((Long)be.size());
+    for (size_t i = 0; i < be.size(); i++) { blk_e[i] = be[i]; blk_t[i] = bt[i]; blk_c[i] = bc[i]; }
+    sctl_cuda::NearBlocks<R> nb(3, 3, blk_e, blk_t, blk_c, elem_nds_cnt, elem_nds_dsp, elem_nds_dsp, near_elem_dsp, K_near_dsp);
+    const Long K_len = (300 * 200 + 400 * 250) * 9;
+    Vector<R> K(K_len), K2(K_len), Unear(450 * 3);
+    for (Long i = 0; i < K_len; i++) K[i] = rnd();
+    nb.SetMatrix(K);
+    nb.SubtractDirect(sl, -1, Xs, Xn, W, Xt);
+    nb.GetMatrix(K2);
+    nb.Apply(Unear, F);
+    R err = 0, mag = 0, uerr = 0, umag = 0;
+    for (Long e = 0; e < 2; e++) {  // reference: one KernelMatrix per element, weights, transpose, subtract; then K * F
+      Vector<R> xs(elem_nds_cnt[e] * 3, &Xs[elem_nds_dsp[e] * 3], false), xt(near_elem_cnt[e] * 3, &Xt[near_elem_dsp[e] * 3], false), none;
+      Matrix<R> M;
+      sl.template KernelMatrix<R, false>(M, xt, xs, none);
+      const Long rows = near_elem_cnt[e] * 3, cols = elem_nds_cnt[e] * 3;
+      for (Long i = 0; i < rows; i++) {
+        R u = 0;
+        for (Long j = 0; j < cols; j++) {
+          const R want = K[K_near_dsp[e] * 9 + i * cols + j] - M(j, i) * W[elem_nds_dsp[e] + j / 3];
+          const R got = K2[K_near_dsp[e] * 9 + i * cols + j];
+          err = std::fmax(err, std::fabs(got - want));
+          mag = std::fmax(mag, std::fabs(want));
+          u += got * F[elem_nds_dsp[e] * 3 + j];
+        }
+        uerr = std::fmax(uerr, std::fabs(u - Unear[near_elem_dsp[e] * 3 + i]));
+        umag = std::fmax(umag, std::fabs(u));
+      }
+    }
+    CHECK(err <= tol * mag);
+    CHECK(uerr <= (sizeof(R) == 8 ? (R)1e-12 : (R)1e-4) * umag);
+  }
+}
+
 int main() {
   std::printf("devices: %d\n", sctl_cuda_device_count());
   generic_kernel_fixtures<double>();
   generic_kernel_fixtures<float>();
   kernel_function_fixtures<double>();
   kernel_function_fixtures<float>();
+  session_layers<double>();
+  session_layers<float>();
   std::printf("\n%s (%d check(s) failed)\n", test_utils::failures == 0 ? "PASS" : "FAIL", test_utils::failures);
   return test_utils::failures == 0 ? 0 : 1;
 }

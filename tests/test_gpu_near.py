@@ -1,0 +1,90 @@
+"""GPU parity tests of the batched near-field blocks: sctl_cuda_near_* against the numpy restatement of
+BoundaryIntegralOp's KNearSubtract / EvalNear loops (oracle/near_blocks.py, boundary_integral.txx:1165-1240,1324-1340)
+on a synthetic block list with the reference's structure: elements own contiguous node ranges, each element has a
+contiguous range of near targets, and the ranges are cut into blocks of at most BLK targets (:1009-1032)."""
+import numpy as np
+import pytest
+
+import cases
+from conftest import TOL, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def block_list(n_elem, k0, k1, seed, blk=37, with_empty=True):
+    """Per-element node counts / near-target counts -> per-block table in the reference's layout."""
+    rng = np.random.RandomState(seed)
+    nds = rng.randint(1, 70, size=n_elem)
+    near = rng.randint(0, 120, size=n_elem)
+    if with_empty:
+        nds[3] = 0      # element without nodes: its blocks write zeros (:1327-1331)
+        near[5] = 0     # element without near targets: no blocks
+    nds_dsp = np.concatenate([[0], np.cumsum(nds)[:-1]])
+    far_dsp = nds_dsp + 11  # far-field nodes live in their own arrays; shifted here to tell the two offsets apart
+    near_dsp = np.concatenate([[0], np.cumsum(near)[:-1]])
+    K_dsp = np.concatenate([[0], np.cumsum(nds * near)[:-1]])  # K_near_dsp (in units of K0*K1 entries)
+    cols = [[] for _ in range(6)]
+    for e in range(n_elem):
+        for t0 in range(0, near[e], blk):
+            n = min(blk, near[e] - t0)
+            for c, v in zip(cols, (nds_dsp[e], far_dsp[e], nds[e], near_dsp[e] + t0, n, K_dsp[e] * k0 * k1 + t0 * k1 * nds[e] * k0)):
+                c.append(v)
+    tab = [np.array(c, dtype=np.int64) for c in cols]
+    return tab, int(nds.sum()), int(far_dsp[-1] + nds[-1]), int(near.sum()), int((nds * near).sum()) * k0 * k1
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", ["Laplace3D_FxU", "Laplace3D_DxU", "Stokes3D_FxU", "Stokes3D_DxU", "Laplace3D_FxdU", "Helmholtz3D_FxU"])
+def test_near_blocks_match_the_reference_loops(sb, cpu_oracle, kernel, dtype):
+    from oracle import near_blocks as nbo
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    tab, n_nodes, n_far, n_trg, K_len = block_list(40, k0, k1, seed=7)
+    Xs, Xn, _, Xt = synth.cube(n_far, n_trg, k0, 3, dtype=dtype)
+    Xn = Xn if nd else None
+    wts = (synth.splitmix_u01(21, n_far) * 0.01 + 0.001).astype(dtype)
+    K0_ = (synth.splitmix_u01(22, K_len) - 0.5).astype(dtype)
+    nb = sb.NearBlocks(sb.KERNELS[kernel], *tab, dtype=dtype)
+    assert (nb.K_len, nb.nU, nb.n_far) == (K_len, n_trg * k1, n_far) and nb.nF <= n_nodes * k0
+    with pytest.raises(sb.SctlCudaError, match="no matrix"):
+        nb.apply(np.zeros(nb.nF, dtype=dtype))
+    nb.set_matrix(K0_)
+    assert np.array_equal(nb.get_matrix(), K0_)
+    # apply on the raw operator: pure batched GEMV
+    F = (synth.splitmix_u01(23, n_nodes * k0) - 0.5).astype(dtype)
+    want_U = nbo.near_apply(k0, k1, tab, K0_.astype(np.float64), F.astype(np.float64), n_trg * k1)
+    U = nb.apply(F)
+    tol = TOL[dtype]
+    assert rel_err(U, want_U) <= (1e-13 if dtype == np.float64 else tol)
+    # subtract the direct part on the device, compare the operator itself and the apply that uses it
+    nb.subtract_direct(Xs, Xn, wts, Xt)
+    want_K = nbo.near_subtract(cpu_oracle, kernel, k0, k1, nd, tab, K0_, Xs, Xn, wts, Xt, dtype=dtype)
+    got_K = nb.get_matrix()
+    assert rel_err(got_K, want_K) <= tol, rel_err(got_K, want_K)
+    U2 = nb.apply(F, U)
+    assert U2 is U
+    assert rel_err(U, nbo.near_apply(k0, k1, tab, want_K.astype(np.float64), F.astype(np.float64), n_trg * k1)) <= tol
+    # rows of an element without nodes are exactly zero; same inputs again give bit-identical results
+    b = int(np.where(tab[2] == 0)[0][0])
+    assert np.all(U[tab[3][b] * k1:(tab[3][b] + tab[4][b]) * k1] == 0)
+    assert np.array_equal(nb.apply(F), U)
+    nb.close()
+
+
+def test_near_blocks_errors_and_empty(sb):
+    e = np.zeros(0, dtype=np.int64)
+    nb = sb.NearBlocks(sb.Laplace3D_FxU, e, e, e, e, e, e)
+    assert (nb.K_len, nb.nF, nb.nU) == (0, 0, 0)
+    nb.set_matrix(np.zeros(0))
+    assert nb.apply(np.zeros(0)).size == 0
+    nb.close()
+    one = np.array([0], dtype=np.int64)
+    nb = sb.NearBlocks(sb.Stokes3D_FxU, one, one, one * 4, one, one * 5, one)
+    nb.set_matrix(np.zeros(nb.K_len))
+    with pytest.raises(sb.SctlCudaError, match="F has"):
+        nb.apply(np.zeros(3))
+    with pytest.raises(sb.SctlCudaError, match="Xs has"):
+        nb.subtract_direct(np.zeros(3), None, np.zeros(1), np.zeros(15))
+    with pytest.raises(sb.SctlCudaError):
+        sb.NearBlocks(sb.Stokes3D_FxU, -one - 1, one, one, one, one, one)
+    nb.close()
