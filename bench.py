@@ -272,14 +272,19 @@ def main():
     my_pairs = float(N) * (t1 - t0)
     k_ms = float(np.mean(ker_ms))
     achieved = my_pairs * F_ALG[kernel] / (k_ms * 1e-3) * 1e-12
-    # DRAM bytes of one pair-kernel launch from the ncu --set full capture of this same workload (profiles/r1_ncu_eval_const_*):
-    # 50.4 MB read + 0.02 MB written per constant-bank launch at 2^20 targets; null for any other workload
-    traffic = 50.43e6 if (kernel, args.log2n, rb, world) == ("Stokes3D_FxU", 20, 8, 1) else None
+    # DRAM bytes of one pair-kernel launch from the ncu --set full capture of this same workload
+    # (profiles/r1_ncu_eval_const_2banks_stokes_fxu_f64.md): 50.38 MB read + 0.02 MB written per constant-bank launch at 2^20
+    # targets (r_trg + the v_trg read-modify-write; the write-back stays in L2); null for any other workload
+    traffic = 50.40e6 if (kernel, args.log2n, rb, world) == ("Stokes3D_FxU", 20, 8, 1) else None
+    const_path = plan["threads"] == 256 and plan["n_launches"] > 10
+    # launches of one Eval on the constant-bank path: pack + 2 probe kernels + one pair kernel per chunk + the bank combine
+    pair_launches = max(1, plan["n_launches"] - 4) if const_path else 1
     roofline = {"bound": "fp64" if rb == 8 else "fp32", "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": traffic,
                 "peak_source": "%s micro-benchmark in this run (sctl_cuda_fma_peak, 1.5 s sustained, FMA = 2 flop); burst 50 ms figure %.2f; MEASURED_PEAKS.json has no FP64/FP32 CUDA-core entry" % ("DFMA" if rb == 8 else "FFMA", peak_burst),
                 "note": "compute-bound on the FP64 CUDA-core pipe (pointwise rsqrt/FMA, ~0 bytes per pair): neither 'hbm' nor 'tensor' applies",
-                "kernel": "eval_pairs%s_kernel<%s, %s>" % ("_const" if plan["threads"] == 256 and plan["n_launches"] > 10 else "", "double" if rb == 8 else "float", kernel),
-                "kernel_ms_per_step": k_ms, "pair_kernel_launches_per_step": max(1, plan["n_launches"] - 3) if plan["n_launches"] > 10 else 1,
+                "kernel": "eval_pairs%s_kernel<%s, %s>" % ("_const" if const_path else "", "double" if rb == 8 else "float", kernel),
+                "kernel_ms_per_step": k_ms, "pair_kernel_launches_per_step": pair_launches,
+                "launch_overlap": "chunk i runs from constant-bank slice i % 2 on its own stream, so consecutive pair-kernel launches overlap; kernel_ms_per_step is the wall time of the whole chain on the device" if const_path else None,
                 "pairs_per_step": my_pairs, "flop_per_pair": F_ALG[kernel],
                 "frac_sctl_flops_convention": my_pairs * SCTL_FLOPS[kernel] / (k_ms * 1e-3) * 1e-12 / peak_sustained,
                 "fp_instr_per_pair": FP_INSTR[kernel], "pipe_ceiling_frac": F_ALG[kernel] / (2.0 * FP_INSTR[kernel])}

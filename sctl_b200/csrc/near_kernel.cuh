@@ -35,17 +35,27 @@ struct NearBlocks {
   const int32_t* item_t0;
 };
 
-constexpr int NEAR_SUB_TRG = 8;    // targets per work item in the subtract kernel
-constexpr int NEAR_APPLY_ROWS = 8; // matrix rows per work item in the apply kernel (one warp per row)
+constexpr int NEAR_SUB_TRG = 32;    // targets per work item in the subtract kernel
+constexpr int NEAR_SUB_THREADS = 128;
+constexpr int NEAR_APPLY_WARPS = 8;  // warps per CTA in the apply kernel
+// rows per warp, processed together (independent loads in flight, F loaded once): 32 bytes of each column step per lane
+template <class Real> __host__ __device__ constexpr int near_apply_rpw() { return 32 / (int)sizeof(Real); }
+template <class Real> __host__ __device__ constexpr int near_apply_rows() { return NEAR_APPLY_WARPS * near_apply_rpw<Real>(); }  // matrix rows per work item
 
 // K_b[(t*K1+k1)][(s*K0+k0)] -= wts[s] * scale * K_{k0,k1}(x_t - x_s, n_s)
-// One CTA per work item (NEAR_SUB_TRG targets of one block); threads stride over the block's sources, so for a fixed
-// row the CTA touches consecutive columns (coalesced read-modify-write).  The pair arithmetic is the KernelMatrix
-// twin PairMatrix<KID> (pair_math.cuh), scaled per entry like generic-kernel.txx:268,306, then by the weight.
+// One CTA per work item (NEAR_SUB_TRG targets of one block).  The CTA's threads are laid out as (source lane, target
+// group): lanes cover the block's sources (for a fixed row they touch consecutive columns: coalesced), groups take
+// alternate targets, so short source lists (64 nodes per element is typical) still use every thread.  The kernel is
+// an HBM read-modify-write stream of K: each thread issues the loads of TU targets' entries before it computes and
+// stores, which keeps several independent DRAM requests in flight per thread (a plain `*p -= x` loop serialises one
+// round trip per target).  The pair arithmetic is the KernelMatrix twin PairMatrix<KID> (pair_math.cuh), scaled per
+// entry like generic-kernel.txx:268,306, then by the weight (:1203).
 template <class Real, int KID, int RSQ>
-__global__ void __launch_bounds__(128) near_subtract_kernel(const NearBlocks nb, const Real* __restrict__ Xs, const Real* __restrict__ Xn, const Real* __restrict__ wts,
-                                                            const Real* __restrict__ Xt, Real* __restrict__ K, Real scale, Real ctx0) {
+__global__ void __launch_bounds__(NEAR_SUB_THREADS) near_subtract_kernel(const NearBlocks nb, const Real* __restrict__ Xs, const Real* __restrict__ Xn, const Real* __restrict__ wts,
+                                                                         const Real* __restrict__ Xt, Real* __restrict__ K, Real scale, Real ctx0) {
   constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
+  constexpr int KK = K0 * K1;
+  constexpr int TU = KK == 1 ? 8 : (KK == 2 ? 4 : (KK <= 4 ? 2 : 1));  // targets whose entries are loaded together
   __shared__ Real xt_s[NEAR_SUB_TRG][3];
   for (int64_t w = blockIdx.x; w < nb.n_items; w += gridDim.x) {
     const int b = nb.item_blk[w];
@@ -53,11 +63,14 @@ __global__ void __launch_bounds__(128) near_subtract_kernel(const NearBlocks nb,
     const int64_t ns = nb.ns[b], nt = nb.nt[b];
     const int n_t = (int)min((int64_t)NEAR_SUB_TRG, nt - t0);
     __syncthreads();
-    if (threadIdx.x < n_t * 3) xt_s[threadIdx.x / 3][threadIdx.x % 3] = Xt[(nb.u_dsp[b] + t0) * 3 + threadIdx.x];
+    if (threadIdx.x < n_t * 3) xt_s[threadIdx.x / 3][threadIdx.x % 3] = Xt[(nb.u_dsp[b] + t0) * 3 + threadIdx.x];  // NEAR_SUB_TRG * 3 <= NEAR_SUB_THREADS
     __syncthreads();
+    int lanes = NEAR_SUB_THREADS;  // source lanes: the smallest power of two >= ns, at least 32 (whole warps share a row)
+    while (lanes > 32 && (lanes >> 1) >= ns) lanes >>= 1;
+    const int groups = NEAR_SUB_THREADS / lanes, grp = threadIdx.x / lanes;
     const int64_t ld = ns * K0;
     Real* Kb = K + nb.k_dsp[b] + t0 * K1 * ld;
-    for (int64_t s = threadIdx.x; s < ns; s += blockDim.x) {
+    for (int64_t s = threadIdx.x % lanes; s < ns; s += lanes) {
       const int64_t gs = nb.far_dsp[b] + s;
       const Real xs[3] = {Xs[gs * 3 + 0], Xs[gs * 3 + 1], Xs[gs * 3 + 2]};
       Real n[3] = {0, 0, 0};
@@ -66,43 +79,86 @@ __global__ void __launch_bounds__(128) near_subtract_kernel(const NearBlocks nb,
         n[1] = Xn[gs * 3 + 1];
         n[2] = Xn[gs * 3 + 2];
       }
-      const Real ws = wts[gs];
-      for (int t = 0; t < n_t; t++) {
-        Real dx[3] = {xt_s[t][0] - xs[0], xt_s[t][1] - xs[1], xt_s[t][2] - xs[2]};
-        const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
-        const Real rinv = rsqrt_masked<RSQ>(r2);
-        Real u[K0 * K1];
-        if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u, dx, rinv, n, r2, ctx0);
-        else PairMatrix<KID, Real>::run(u, dx, rinv, n);
+      const Real ws = wts[gs] * scale;
+      for (int tb = grp * TU; tb < n_t; tb += groups * TU) {
+        Real old[TU][KK];
 #pragma unroll
-        for (int k1 = 0; k1 < K1; k1++)
+        for (int j = 0; j < TU; j++)
+          if (tb + j < n_t) {
 #pragma unroll
-          for (int k0 = 0; k0 < K0; k0++) {
-            Real* p = Kb + (int64_t)(t * K1 + k1) * ld + s * K0 + k0;
-            *p -= (u[k0 * K1 + k1] * scale) * ws;  // KernelMatrix entry (scaled), times the weight (:1203), subtracted (:1228)
+            for (int k1 = 0; k1 < K1; k1++)
+#pragma unroll
+              for (int k0 = 0; k0 < K0; k0++) old[j][k0 * K1 + k1] = Kb[(int64_t)((tb + j) * K1 + k1) * ld + s * K0 + k0];
+          }
+#pragma unroll
+        for (int j = 0; j < TU; j++)
+          if (tb + j < n_t) {
+            const int t = tb + j;
+            Real dx[3] = {xt_s[t][0] - xs[0], xt_s[t][1] - xs[1], xt_s[t][2] - xs[2]};
+            const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
+            const Real rinv = rsqrt_masked<RSQ>(r2);
+            Real u[KK];
+            if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u, dx, rinv, n, r2, ctx0);
+            else PairMatrix<KID, Real>::run(u, dx, rinv, n);
+#pragma unroll
+            for (int k1 = 0; k1 < K1; k1++)
+#pragma unroll
+              for (int k0 = 0; k0 < K0; k0++) Kb[(int64_t)(t * K1 + k1) * ld + s * K0 + k0] = fma(-u[k0 * K1 + k1], ws, old[j][k0 * K1 + k1]);
           }
       }
     }
   }
 }
 
-// U_b[r] = sum_c K_b[r][c] * F_b[c]; one warp per row, lanes stride the columns, fixed shuffle tree (deterministic).
-// Blocks with no sources write zeros (boundary_integral.txx:1327-1331).
+// U_b[r] = sum_c K_b[r][c] * F_b[c].  A warp owns RPW consecutive rows and walks the columns once, two column steps per
+// iteration: per iteration two F values and 2*RPW matrix values per lane, all independent loads; fixed summation order
+// and shuffle tree per row (deterministic).  Blocks with no sources write zeros (boundary_integral.txx:1327-1331).
 template <class Real>
-__global__ void __launch_bounds__(32 * NEAR_APPLY_ROWS) near_apply_kernel(const NearBlocks nb, int K0, int K1, const Real* __restrict__ K, const Real* __restrict__ F, Real* __restrict__ U) {
+__global__ void __launch_bounds__(32 * NEAR_APPLY_WARPS) near_apply_kernel(const NearBlocks nb, int K0, int K1, const Real* __restrict__ K, const Real* __restrict__ F, Real* __restrict__ U) {
+  constexpr int RPW = near_apply_rpw<Real>();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t w = blockIdx.x; w < nb.n_items; w += gridDim.x) {
     const int b = nb.item_blk[w];
-    const int64_t r = (int64_t)nb.item_t0[w] + warp;  // row of the block's matrix
+    const int64_t r0 = (int64_t)nb.item_t0[w] + warp * RPW;  // first row of this warp in the block's matrix
     const int64_t rows = nb.nt[b] * K1, cols = nb.ns[b] * K0;
-    if (r >= rows) continue;
-    const Real* Kr = K + nb.k_dsp[b] + r * cols;
+    if (r0 >= rows) continue;
+    const Real* Kr = K + nb.k_dsp[b] + r0 * cols;
     const Real* Fb = F + nb.f_dsp[b] * K0;
-    Real acc = 0;
-    for (int64_t c = lane; c < cols; c += 32) acc = fma(Kr[c], Fb[c], acc);
+    const int nr = (int)min((int64_t)RPW, rows - r0);
+    Real acc[RPW];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) U[nb.u_dsp[b] * K1 + r] = acc;
+    for (int j = 0; j < RPW; j++) acc[j] = 0;
+    int64_t c = lane;
+    if (nr == RPW) {
+      for (; c + 32 < cols; c += 64) {
+        const Real f0 = Fb[c], f1 = Fb[c + 32];
+        Real k0v[RPW], k1v[RPW];
+#pragma unroll
+        for (int j = 0; j < RPW; j++) {
+          k0v[j] = Kr[j * cols + c];
+          k1v[j] = Kr[j * cols + c + 32];
+        }
+#pragma unroll
+        for (int j = 0; j < RPW; j++) acc[j] = fma(k1v[j], f1, fma(k0v[j], f0, acc[j]));
+      }
+    }
+    for (; c < cols; c += 32) {
+      const Real f = Fb[c];
+#pragma unroll
+      for (int j = 0; j < RPW; j++)
+        if (j < nr) acc[j] = fma(Kr[j * cols + c], f, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < RPW; j++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if (lane < nr) {
+      Real v = acc[0];
+#pragma unroll
+      for (int j = 1; j < RPW; j++) v = (lane == j) ? acc[j] : v;
+      U[nb.u_dsp[b] * K1 + r0 + lane] = v;
+    }
   }
 }
 

@@ -78,13 +78,14 @@ def test_near_blocks_errors_and_empty(sb):
     nb.set_matrix(np.zeros(0))
     assert nb.apply(np.zeros(0)).size == 0
     nb.close()
-    one = np.array([0], dtype=np.int64)
-    nb = sb.NearBlocks(sb.Stokes3D_FxU, one, one, one * 4, one, one * 5, one)
+    one, i64 = np.array([0], dtype=np.int64), lambda v: np.array([v], dtype=np.int64)
+    nb = sb.NearBlocks(sb.Stokes3D_FxU, one, one, i64(4), one, i64(5), one)
+    assert (nb.K_len, nb.nF, nb.nU, nb.n_far) == (4 * 5 * 9, 12, 15, 4)
     nb.set_matrix(np.zeros(nb.K_len))
     with pytest.raises(sb.SctlCudaError, match="F has"):
         nb.apply(np.zeros(3))
     with pytest.raises(sb.SctlCudaError, match="Xs has"):
         nb.subtract_direct(np.zeros(3), None, np.zeros(1), np.zeros(15))
     with pytest.raises(sb.SctlCudaError):
-        sb.NearBlocks(sb.Stokes3D_FxU, -one - 1, one, one, one, one, one)
+        sb.NearBlocks(sb.Stokes3D_FxU, i64(-1), one, one, one, one, one)
     nb.close()
