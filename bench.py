@@ -114,6 +114,12 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line (rank 0): everything else that libraries print to fd 1 (NCCL's version banner
+    # when the box sets NCCL_DEBUG=VERSION, torch warnings) is sent to stderr from here on
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -140,7 +146,8 @@ def main():
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
                 "config": config, "cpu_baseline": info, "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0, "note": "reference CPU arm: SCTL's own OpenMP/Vec<> Eval on the host cores, bounded target sample per step"}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
         return
 
     import torch
@@ -156,8 +163,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, world)
 
@@ -304,7 +309,8 @@ def main():
         line["parity"] = {"max_abs_err_over_vinf": float(np.abs(got.astype(np.float64) - cpu_res.astype(np.float64)).max() / np.abs(full.cpu().numpy()).max()),
                           "gate": 1e-12 if rb == 8 else "1e-5 for Ns <= 2^14; beyond that two FP32 summation orders differ by more (SURVEY 7.3)",
                           "checked": "%d strided targets x all sources vs the CPU arm above" % nsub}
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

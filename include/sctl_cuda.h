@@ -173,12 +173,14 @@ int sctl_cuda_near_subtract_direct(sctl_cuda_near_t h, int kernel_id, int digits
 int sctl_cuda_near_apply(sctl_cuda_near_t h, const void* F, int64_t nF, void* U, int64_t nU);
 
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
- *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks
- *                       (FP64 only unless "const_fp32" is set to 1);
+ *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64;
+ *                       FP32 per "const_fp32": 0 never, 1 always, -1 (default) for Nt >= 2^17 and every kernel but
+ *                       Laplace3D_FxU, where it measured faster than the shared-memory ring);
  *   "wide_min_targets"  (default 2^16): at or above (FP64), 4 targets per thread, one CTA per SM;
  *   "few_max_targets"   (default 2048): at or below, the warps of a CTA share 32 targets and split the sources.
- *   "const_banks"       (default 2): slices of the constant buffer in flight on the constant-bank path; chunk i
- *                       streams through slice i % banks on its own stream so consecutive launches overlap (1..4);
+ *   "const_banks" / "const_banks_fp32" (defaults 2 / 4): slices of the constant buffer in flight on the constant-bank
+ *                       path (FP64 / FP32); chunk i streams through slice i % banks on its own stream so consecutive
+ *                       launches overlap (1..4);
  *   "const_ctas_per_sm" / "const_ctas_per_sm_overlap" (defaults 6 / 1): CTAs per SM a launch should have before its
  *                       chunk is split across a thread-block cluster (one launch at a time / overlapping launches);
  *   "probe_min_pairs"   (default 2e9): at or above Ns*Nt, Eval first checks (O(Ns+Nt), on the device) whether any source

@@ -36,6 +36,8 @@ template <class Real> struct ConstEvalArgs {
   int64_t Nt;
   int n_rec;          // records in the constant bank for this launch
   int sub_len;        // records per cluster rank (grid.y slice)
+  int full_ranks;     // n_rec / sub_len: ranks with a full slice
+  int tail_len;       // n_rec % sub_len: records of rank `full_ranks`
   int bank_off;       // first Real of this launch's bank inside c_src_pack (multi-bank streaming, see below)
   int allow_unmasked; // this call ran the coincidence probe: c_eval_must_mask is meaningful
   Real scale;
@@ -73,7 +75,9 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
   }
   // Loop bounds are kept in a form ptxas recognises as warp-uniform, otherwise it falls back to vector LDC.
   const Real* src = reinterpret_cast<const Real*>(c_src_pack) + a.bank_off + (int)blockIdx.y * a.sub_len * REC;
-  const int n = (blockIdx.y + 1 == gridDim.y) ? a.n_rec - (int)blockIdx.y * a.sub_len : a.sub_len;
+  // ranks [0, full_ranks) take sub_len records, rank full_ranks the remainder, later ranks nothing (a short last chunk
+  // can have fewer records than the cluster has ranks); all three come from the host so the bound stays uniform
+  const int n = ((int)blockIdx.y < a.full_ranks) ? a.sub_len : (((int)blockIdx.y == a.full_ranks) ? a.tail_len : 0);
   if (a.allow_unmasked && c_eval_must_mask[0] == 0) {
 #pragma unroll U
     for (int s = 0; s < n; s++) {

@@ -102,7 +102,11 @@ struct Options {
   int64_t const_banks = 2;
   int64_t const_ctas_per_sm = 6;
   int64_t const_ctas_per_sm_overlap = 1;
-  int64_t const_fp32 = 0;  // FP32 gains nothing from the constant-bank path (rates in profiles/): off by default
+  // FP32 on the constant-bank path: 0 never, 1 always (above const_min_targets), -1 (default) where it measured faster
+  // than the shared-memory ring (profiles/r1_fp32_paths.md): Nt >= 2^17 and every kernel but Laplace3D_FxU, with
+  // const_banks_fp32 slices in flight (FP32 launches are half as long, so four slices hide their boundaries better)
+  int64_t const_fp32 = -1;
+  int64_t const_banks_fp32 = 4;
   // Above this many pairs Eval first runs the O(Ns+Nt) coincidence probe (coincidence.cuh) and lets the pair kernels
   // drop the r2 == 0 mask when no source/target pair can need it.  <= 0 disables the probe (always mask).
   int64_t probe_min_pairs = 2000000000LL;
@@ -278,7 +282,7 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   if (n_tb > 2147483647LL) return fail("too many target blocks");
   DeviceInfo& di = g.dev[dev];
   // Banks: chunk i streams through slice i % banks of the constant buffer on its own stream (eval_const_kernel.cuh).
-  int banks = (int)std::max<int64_t>(1, std::min<int64_t>(g.opt.const_banks, CONST_MAX_BANKS));
+  int banks = (int)std::max<int64_t>(1, std::min<int64_t>(sizeof(Real) == 8 ? g.opt.const_banks : g.opt.const_banks_fp32, CONST_MAX_BANKS));
   const int CH = const_bank_records<Real, KID>(banks);
   if ((Ns + CH - 1) / CH < 2 * banks) banks = 1;  // too few chunks to pipeline
   const int CHB = const_bank_records<Real, KID>(banks);
@@ -336,6 +340,8 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
     a.v_trg = b ? alt + (size_t)(b - 1) * nv : v_trg;
     a.n_rec = n;
     a.sub_len = (n + cl - 1) / cl;
+    a.full_ranks = n / a.sub_len;
+    a.tail_len = n % a.sub_len;
     a.bank_off = b * bank_stride;
     cfg.stream = st;
     CU_TRY(cudaLaunchKernelEx(&cfg, kern, a));
@@ -390,7 +396,8 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
     n_probe_launches = 2;
   }
   int rc;
-  if (Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || g.opt.const_fp32))
+  const bool fp32_const = g.opt.const_fp32 == 1 || (g.opt.const_fp32 < 0 && Nt >= (1 << 17) && KID != LAPLACE3D_FXU);
+  if (Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || fp32_const))
     rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream);
   else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8 && KerTraits<KID>::K1 <= 4)  // 9 accumulators x 4 targets would spill
     rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream, 8 * Tn::WIDE_TILE, 64);
@@ -947,6 +954,7 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "wide_min_targets")) g.opt.wide_min_targets = value;
   else if (!strcmp(name, "const_fp32")) g.opt.const_fp32 = value;
   else if (!strcmp(name, "const_banks")) g.opt.const_banks = value;
+  else if (!strcmp(name, "const_banks_fp32")) g.opt.const_banks_fp32 = value;
   else if (!strcmp(name, "const_ctas_per_sm")) g.opt.const_ctas_per_sm = value;
   else if (!strcmp(name, "const_ctas_per_sm_overlap")) g.opt.const_ctas_per_sm_overlap = value;
   else if (!strcmp(name, "probe_min_pairs")) g.opt.probe_min_pairs = value;

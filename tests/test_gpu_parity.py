@@ -42,7 +42,9 @@ def test_kernel_matrix_matches_reference_golden(sb, golden, kernel, dtype):
 # Shapes chosen around the kernel's internal boundaries: 32*T target groups, the few-target threshold (2048),
 # the 512-target CTA, tile lengths 256/512 and chunk splits; plus ragged and degenerate sizes.
 SHAPES = [(1, 1), (2, 31), (255, 32), (256, 33), (257, 511), (513, 512), (1023, 513), (4097, 2047), (4099, 2048), (3001, 2049),
-          (16384, 4100), (777, 10000), (40000, 300), (5, 20000)]
+          (16384, 4100), (777, 10000), (40000, 300), (5, 20000),
+          # constant-bank path (Nt >= 2^15): fewer sources than cluster ranks, one chunk, a few chunks + ragged tail
+          (5, 40000), (1, 32768), (700, 33001), (3100, 32800)]
 
 
 @pytest.mark.parametrize("dtype", DTYPES)

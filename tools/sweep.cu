@@ -222,6 +222,8 @@ void run_const(Ctx& c, int n_sub = 1, int wpc = 0) {
       CK(cudaMemcpyToSymbolAsync(c_src_pack, (const Real*)c.pack + s0 * REC, sizeof(Real) * n * REC, 0, cudaMemcpyDeviceToDevice));
       a.n_rec = n;
       a.sub_len = (n + n_sub - 1) / n_sub;
+      a.full_ranks = n / a.sub_len;
+      a.tail_len = n % a.sub_len;
       CK(cudaLaunchKernelEx(&cfg, kern, a));
       launches++;
     }
@@ -261,6 +263,8 @@ void run_const_breakdown(Ctx& c) {
   a.scale = scale_factor<Real>(KID);
   a.n_rec = CH;
   a.sub_len = CH;
+  a.full_ranks = 1;
+  a.tail_len = 0;
   const int tpb = NT * T;
   dim3 grid((unsigned)((c.Nt + tpb - 1) / tpb), 1);
   const int n_launch = (int)((c.Ns + CH - 1) / CH);
