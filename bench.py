@@ -77,13 +77,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_arm(kernel, N, nsub, steps, warmup, want_result=False, dtype=np.float64):
+def cpu_arm(kernel, N, nsub, steps, warmup, want_result=False, dtype=np.float64, points="cube", log2n=0):
     """The reference's CPU Eval on all N sources x nsub strided targets; returns (pairs/s, info, subset result)."""
     import oracle
     from sctl_b200 import synth
     orc = oracle.best_cpu_oracle()
     k0, k1, nd = DIMS[kernel]
     r_src, n_src, v_src, r_trg = synth.cube(N, N, k0, nd, dtype=dtype)
+    if points == "torus":
+        X, Nrm, _, _ = synth.torus(1 << ((log2n + 1) // 2), 1 << (log2n // 2), dtype=dtype)
+        r_src, r_trg, n_src = X, X, (Nrm if nd else None)
     idx = np.arange(nsub) * (N // nsub)
     sub = np.ascontiguousarray(r_trg.reshape(-1, 3)[idx]).reshape(-1)
     for _ in range(max(warmup, 2)):  # the reference's first calls pay OpenMP start-up and its scratch-pool first touch
@@ -108,6 +111,8 @@ def main():
     ap.add_argument("--kernel", default="Stokes3D_FxU", choices=list(DIMS))
     ap.add_argument("--log2n", type=int, default=20, help="Ns = Nt = 2^log2n (BASELINE: 20)")
     ap.add_argument("--digits", type=int, default=-1)
+    ap.add_argument("--points", default="cube", choices=["cube", "torus"],
+                    help="cube: sources and targets uniform in the unit cube, distinct sets (BASELINE); torus: surface points, targets == sources (every target has one r2 == 0 pair)")
     ap.add_argument("--real", default="f64", choices=["f64", "f32"], help="arithmetic type (BASELINE metric: f64; configs[3] also names f32)")
     ap.add_argument("--cpu-targets", type=int, default=1 << 14, help="strided target subsample for the CPU baseline / parity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -132,6 +137,8 @@ def main():
     rb = 8 if args.real == "f64" else 4
     workload = "%s GenericKernel::Eval %s, Ns=Nt=2^%d uniform in unit cube%s" % (kernel, "FP64" if rb == 8 else "FP32", args.log2n,
                                                                                  " (BASELINE configs[2])" if (kernel, args.log2n, rb) == ("Stokes3D_FxU", 20, 8) else "")
+    if args.points == "torus":
+        workload = workload.replace("uniform in unit cube", "torus surface nodes (R=1, a=0.25, %d x %d grid), targets == sources" % (1 << ((args.log2n + 1) // 2), 1 << (args.log2n // 2)))
     config = {"workload": workload, "kernel": kernel, "Ns": N, "Nt": N, "digits": args.digits, "inputs": "SplitMix64 streams (SURVEY 8d), generated in f64%s" % ("" if rb == 8 else ", cast to f32"),
               "sharding": "targets by contiguous block over %d GPU(s), sources replicated by NCCL broadcast" % args.gpus,
               "l2": "a 256 MiB buffer is overwritten between timed steps (L2 flush)"}
@@ -140,7 +147,7 @@ def main():
         if rank != 0:
             return
         nsub = min(N, 1 << 13)
-        val, info, _, sec = cpu_arm(kernel, N, nsub, args.steps, args.warmup, dtype=npdt)
+        val, info, _, sec = cpu_arm(kernel, N, nsub, args.steps, args.warmup, dtype=npdt, points=args.points, log2n=args.log2n)
         info["value"] = val
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.real, "data": "synthetic",
@@ -170,6 +177,10 @@ def main():
     s0, s1 = block_range(N, rank, world)
     t0, t1 = block_range(N, rank, world)
     r_src, n_src, v_src, r_trg = synth.cube(s1 - s0, t1 - t0, k0, nd, dtype=npdt, first_src=s0, first_trg=t0)
+    if args.points == "torus":  # surface-point set; coordinates and normals from the torus, densities as above
+        X, Nrm, _, _ = synth.torus(1 << ((args.log2n + 1) // 2), 1 << (args.log2n // 2), dtype=npdt)
+        r_src, r_trg = X[s0 * 3:s1 * 3].copy(), X[t0 * 3:t1 * 3].copy()
+        n_src = Nrm[s0 * 3:s1 * 3].copy() if nd else None
     tdt = torch.float64 if rb == 8 else torch.float32
     pin = lambda a: None if a is None else torch.from_numpy(a).pin_memory()
     h_r_src, h_n_src, h_v_src, h_r_trg = pin(r_src), pin(n_src), pin(v_src), pin(r_trg)
@@ -302,7 +313,7 @@ def main():
 
     if not args.no_cpu_baseline and world == 1:
         nsub = min(N, args.cpu_targets)
-        val, info, (idx, cpu_res), _ = cpu_arm(kernel, N, nsub, 2, 2, want_result=True, dtype=npdt)
+        val, info, (idx, cpu_res), _ = cpu_arm(kernel, N, nsub, 2, 2, want_result=True, dtype=npdt, points=args.points, log2n=args.log2n)
         info.update({"value": val, "unit": UNIT})
         line["cpu_baseline"] = info
         got = full.cpu().numpy().reshape(-1, k1)[idx].reshape(-1)

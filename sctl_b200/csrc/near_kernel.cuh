@@ -110,11 +110,12 @@ __global__ void __launch_bounds__(NEAR_SUB_THREADS) near_subtract_kernel(const N
   }
 }
 
-// U_b[r] = sum_c K_b[r][c] * F_b[c].  A warp owns RPW consecutive rows and walks the columns once, two column steps per
-// iteration: per iteration two F values and 2*RPW matrix values per lane, all independent loads; fixed summation order
-// and shuffle tree per row (deterministic).  Blocks with no sources write zeros (boundary_integral.txx:1327-1331).
+// U_b[r] = sum_c K_b[r][c] * F_b[c].  A warp owns RPW consecutive rows and walks the columns once: per step one F value
+// and RPW matrix values per lane, all independent loads; fixed summation order and shuffle tree per row
+// (deterministic).  Register use is capped so that five (FP64) or four (FP32, eight rows per warp) CTAs stay resident per SM: the kernel is a latency-bound
+// stream of short rows and needs the bytes in flight.  Blocks with no sources write zeros (boundary_integral.txx:1327-1331).
 template <class Real>
-__global__ void __launch_bounds__(32 * NEAR_APPLY_WARPS) near_apply_kernel(const NearBlocks nb, int K0, int K1, const Real* __restrict__ K, const Real* __restrict__ F, Real* __restrict__ U) {
+__global__ void __launch_bounds__(32 * NEAR_APPLY_WARPS, (sizeof(Real) == 8 ? 5 : 4)) near_apply_kernel(const NearBlocks nb, int K0, int K1, const Real* __restrict__ K, const Real* __restrict__ F, Real* __restrict__ U) {
   constexpr int RPW = near_apply_rpw<Real>();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int64_t w = blockIdx.x; w < nb.n_items; w += gridDim.x) {
@@ -128,25 +129,21 @@ __global__ void __launch_bounds__(32 * NEAR_APPLY_WARPS) near_apply_kernel(const
     Real acc[RPW];
 #pragma unroll
     for (int j = 0; j < RPW; j++) acc[j] = 0;
-    int64_t c = lane;
+    const int icols = (int)cols;  // a block row fits 32 bits; keeps the per-row offsets out of 64-bit registers
+    const Real* p = Kr + lane;
     if (nr == RPW) {
-      for (; c + 32 < cols; c += 64) {
-        const Real f0 = Fb[c], f1 = Fb[c + 32];
-        Real k0v[RPW], k1v[RPW];
+      for (int c = lane; c < icols; c += 32, p += 32) {
+        const Real f = Fb[c];
 #pragma unroll
-        for (int j = 0; j < RPW; j++) {
-          k0v[j] = Kr[j * cols + c];
-          k1v[j] = Kr[j * cols + c + 32];
-        }
-#pragma unroll
-        for (int j = 0; j < RPW; j++) acc[j] = fma(k1v[j], f1, fma(k0v[j], f0, acc[j]));
+        for (int j = 0; j < RPW; j++) acc[j] = fma(p[j * icols], f, acc[j]);
       }
-    }
-    for (; c < cols; c += 32) {
-      const Real f = Fb[c];
+    } else {
+      for (int c = lane; c < icols; c += 32, p += 32) {
+        const Real f = Fb[c];
 #pragma unroll
-      for (int j = 0; j < RPW; j++)
-        if (j < nr) acc[j] = fma(Kr[j * cols + c], f, acc[j]);
+        for (int j = 0; j < RPW; j++)
+          if (j < nr) acc[j] = fma(p[j * icols], f, acc[j]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < RPW; j++) {

@@ -96,6 +96,7 @@ def test_constant_bank_path_all_kernels(sb, cpu_oracle, kernel, dtype):
         sb.set_option("const_fp32", 1)  # the FP32 instantiations exist and must be right even though FP64 alone uses them by default
         for (banks, ov), grid_y in CONST_CONFIGS:
             sb.set_option("const_banks", banks)
+            sb.set_option("const_banks_fp32", banks)
             sb.set_option("const_ctas_per_sm_overlap", ov)
             d_v = torch.from_numpy(pre).cuda()
             sb.eval_device(sb.KERNELS[kernel], d[0], d[1], d[2], d[3], d_v)
