@@ -34,8 +34,24 @@ template <class Real> __device__ __forceinline__ uint64_t point_key(const Real* 
   return k ? k : 1;  // 0 marks an empty slot
 }
 
-// table: (mask + 1) zero-initialised 64-bit slots, mask + 1 = power of two >= 2 * Ns
-template <class Real> __global__ void coincidence_insert_kernel(int64_t Ns, const Real* __restrict__ r_src, unsigned long long* table, uint64_t mask) {
+// Per-block refinement (constant-bank path).  Coincident pairs are rare even when they exist -- targets == sources has
+// one per target -- so the probe can also say WHERE they are: the insert pass records, per hash slot, the range of
+// source CHUNKS (constant-bank launches) holding that point, and a target that hits a slot raises one bit per
+// (chunk, target block) in `bits` (chunk-major rows of `row_words` 32-bit words, at `bits + chunk * row_stride`).  A
+// CTA of launch c then takes the unmasked loop unless its own bit in row c is set.  A point duplicated over more than
+// MAX_CHUNK_SPAN chunks gives up on the refinement (flag[1]) and the global flag alone decides.
+struct CoincidenceBits {
+  unsigned* bits;       // nullptr: no refinement
+  int64_t row_stride;   // 32-bit words between the rows of consecutive chunks
+  int64_t chunk_len;    // sources per chunk
+  int64_t trg_per_blk;  // targets per CTA (one bit each)
+  unsigned* cmin;       // [slots] first / last chunk holding the slot's point
+  unsigned* cmax;
+};
+constexpr unsigned MAX_CHUNK_SPAN = 8;
+
+// table: (mask + 1) zero-initialised 64-bit slots, mask + 1 = power of two >= 2 * Ns; cmin initialised to 0xFFFFFFFF, cmax to 0
+template <class Real> __global__ void coincidence_insert_kernel(int64_t Ns, const Real* __restrict__ r_src, unsigned long long* table, uint64_t mask, const CoincidenceBits cb) {
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < Ns; s += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t key = point_key(r_src + s * 3);
     uint64_t slot = key & mask;
@@ -44,12 +60,18 @@ template <class Real> __global__ void coincidence_insert_kernel(int64_t Ns, cons
       if (prev == 0ULL || prev == key) break;
       slot = (slot + 1) & mask;
     }
+    if (cb.bits) {
+      const unsigned c = (unsigned)(s / cb.chunk_len);
+      atomicMin(&cb.cmin[slot], c);
+      atomicMax(&cb.cmax[slot], c);
+    }
   }
 }
 
-// must_mask[0] becomes 1 when some target's key is in the table
+// flag[0] becomes 1 when some target's key is in the table; flag[1] when the per-block refinement cannot be trusted
 template <class Real>
-__global__ void coincidence_probe_kernel(int64_t Nt, const Real* __restrict__ r_trg, const unsigned long long* __restrict__ table, uint64_t mask, int* must_mask) {
+__global__ void coincidence_probe_kernel(int64_t Nt, const Real* __restrict__ r_trg, const unsigned long long* __restrict__ table, uint64_t mask, int* flag,
+                                         const CoincidenceBits cb) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < Nt; t += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t key = point_key(r_trg + t * 3);
     uint64_t slot = key & mask;
@@ -57,7 +79,16 @@ __global__ void coincidence_probe_kernel(int64_t Nt, const Real* __restrict__ r_
       const unsigned long long v = table[slot];
       if (v == 0ULL) break;
       if (v == key) {
-        must_mask[0] = 1;
+        flag[0] = 1;
+        if (cb.bits) {
+          const unsigned c0 = cb.cmin[slot], c1 = cb.cmax[slot];
+          if (c1 - c0 >= MAX_CHUNK_SPAN) {
+            flag[1] = 1;
+          } else {
+            const int64_t b = t / cb.trg_per_blk;
+            for (unsigned c = c0; c <= c1; c++) atomicOr(cb.bits + (int64_t)c * cb.row_stride + (b >> 5), 1u << (b & 31));
+          }
+        }
         break;
       }
       slot = (slot + 1) & mask;

@@ -26,7 +26,7 @@ namespace sctl_cuda {
 constexpr int CONST_PACK_BYTES = 64 * 1024 - 1024;  // leave room for the compiler's own bank-3 constants
 __constant__ double c_src_pack[CONST_PACK_BYTES / 8];
 // [0]: the coincidence probe's verdict for the call in flight (0 = no source/target pair can have r2 < 2^-1022, so the
-// unmasked loop is exact).  Copied device-to-device from the probe's flag, so the choice needs no host round trip, and
+// unmasked loop is exact); [1]: 1 = the per-CTA bits that refine a verdict of 1 are not usable.  Copied device-to-device from the probe's flag, so the choice needs no host round trip, and
 // read with LDCU, so the branch on it is uniform and the loops keep their uniform-register operands.
 __constant__ int c_eval_must_mask[4];
 
@@ -39,6 +39,7 @@ template <class Real> struct ConstEvalArgs {
   int full_ranks;     // n_rec / sub_len: ranks with a full slice
   int tail_len;       // n_rec % sub_len: records of rank `full_ranks`
   int bank_off;       // first Real of this launch's bank inside c_src_pack (multi-bank streaming, see below)
+  int bits_off;       // first 32-bit word of this launch's coincidence bits inside c_src_pack (one bit per CTA), -1: none
   int allow_unmasked; // this call ran the coincidence probe: c_eval_must_mask is meaningful
   Real scale;
   Real ctx0;          // kernel context by value (Helmholtz wavenumber)
@@ -51,8 +52,34 @@ template <class Real, int KID> constexpr int const_chunk_records() { return CONS
 // over the SMs as chunk i's last wave drains -- no idle tail and no wave quantisation per launch.  Launches that
 // share a slice are ordered by their stream; launches of different slices accumulate into different buffers.
 constexpr int CONST_MAX_BANKS = 4;
-template <class Real, int KID> inline int const_bank_records(int banks) {
-  return (CONST_PACK_BYTES / banks / 16 * 16) / (RecTraits<Real, KID>::REC * (int)sizeof(Real));
+
+// Geometry of one call: how the constant buffer is cut and how the packed sources are laid out in HBM.  Every chunk is
+// a SEGMENT of seg_bytes: `chunk` records followed (when the call carries coincidence bits) by `row_words` 32-bit words
+// with one bit per target block; a launch copies one segment into its slice with one cudaMemcpyToSymbolAsync.
+struct ConstGeom {
+  int banks;            // slices in flight
+  int chunk;            // records per launch
+  int row_words;        // 32-bit words of coincidence bits per chunk (0: none), a multiple of 4
+  int bank_stride;      // bytes between slices in c_src_pack
+  int rec_bytes;
+  int64_t seg_bytes;
+  int64_t n_chunks;
+};
+template <class Real, int KID> inline ConstGeom const_geometry(int64_t Ns, int64_t n_tblocks, int banks_wanted, bool want_bits) {
+  ConstGeom g;
+  g.rec_bytes = RecTraits<Real, KID>::REC * (int)sizeof(Real);
+  for (int pass = 0;; pass++) {
+    g.banks = pass ? 1 : banks_wanted;
+    g.bank_stride = CONST_PACK_BYTES / g.banks / 16 * 16;
+    const int64_t words = (n_tblocks + 31) / 32;
+    g.row_words = (want_bits && words * 4 <= g.bank_stride / 8) ? (int)((words + 3) / 4 * 4) : 0;  // bits take at most 1/8 of a slice
+    g.chunk = (g.bank_stride - g.row_words * 4) / g.rec_bytes;
+    g.n_chunks = (Ns + g.chunk - 1) / g.chunk;
+    if (g.banks == 1 || g.n_chunks >= 2 * g.banks) break;  // too few chunks to pipeline: one slice
+  }
+  if (g.n_chunks > 0xFFFFFFF0LL) g.row_words = 0;  // chunk numbers are kept in 32 bits by the probe
+  g.seg_bytes = (int64_t)g.chunk * g.rec_bytes + g.row_words * 4;
+  return g;
 }
 
 // NT is the LARGEST block the kernel may be launched with; the host picks blockDim.x = 32 * (warps per CTA) <= NT so
@@ -78,7 +105,19 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
   // ranks [0, full_ranks) take sub_len records, rank full_ranks the remainder, later ranks nothing (a short last chunk
   // can have fewer records than the cluster has ranks); all three come from the host so the bound stays uniform
   const int n = ((int)blockIdx.y < a.full_ranks) ? a.sub_len : (((int)blockIdx.y == a.full_ranks) ? a.tail_len : 0);
-  if (a.allow_unmasked && c_eval_must_mask[0] == 0) {
+  // Masked or unmasked loop (bit-identical results wherever no pair has r2 < 2^-1022): unmasked when the probe found no
+  // coincident source/target pair at all, or -- targets == sources is the common case with one such pair per target --
+  // none between THIS CTA's targets and THIS launch's chunk (coincidence.cuh).  Every operand of the decision comes
+  // from the constant bank or blockIdx, so the branch is uniform and both loops keep their LDCU operands.
+  bool unmasked = false;
+  if (a.allow_unmasked) {
+    unmasked = c_eval_must_mask[0] == 0;
+    if (!unmasked && a.bits_off >= 0 && c_eval_must_mask[1] == 0) {
+      const unsigned w = reinterpret_cast<const unsigned*>(c_src_pack)[a.bits_off + (int)(blockIdx.x >> 5)];
+      unmasked = ((w >> (blockIdx.x & 31)) & 1u) == 0;
+    }
+  }
+  if (unmasked) {
 #pragma unroll U
     for (int s = 0; s < n; s++) {
       const Real* rec = src + s * REC;  // uniform address: LDCU into uniform registers

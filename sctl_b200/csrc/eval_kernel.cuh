@@ -71,7 +71,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // ------------------------------------------------------------------------------------------------
 template <class Real, int KID>
 __global__ void pack_sources_kernel(int64_t Ns, const Real* __restrict__ r_src, const Real* __restrict__ n_src,
-                                    const Real* __restrict__ v_src, Real* __restrict__ pack) {
+                                    const Real* __restrict__ v_src, Real* __restrict__ pack, int64_t chunk_len, int64_t seg_reals) {
   constexpr int REC = RecTraits<Real, KID>::REC;
   constexpr int K0 = KerTraits<KID>::K0;
   for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < Ns; s += (int64_t)gridDim.x * blockDim.x) {
@@ -92,8 +92,11 @@ __global__ void pack_sources_kernel(int64_t Ns, const Real* __restrict__ r_src, 
         for (int k = 0; k < 3; k++) rec[3 + K0 + k] = n_src[s * 3 + k];
       }
     }
+    // contiguous records (chunk_len >= Ns), or chunk-strided segments for the constant-bank path: records of chunk c at
+    // pack + c * seg_reals, followed by that chunk's coincidence bits (coincidence.cuh), so one copy moves both
+    Real* dst = pack + (s / chunk_len) * seg_reals + (s % chunk_len) * REC;
 #pragma unroll
-    for (int k = 0; k < REC; k++) pack[s * REC + k] = rec[k];
+    for (int k = 0; k < REC; k++) dst[k] = rec[k];
   }
 }
 

@@ -110,6 +110,9 @@ struct Options {
   // Above this many pairs Eval first runs the O(Ns+Nt) coincidence probe (coincidence.cuh) and lets the pair kernels
   // drop the r2 == 0 mask when no source/target pair can need it.  <= 0 disables the probe (always mask).
   int64_t probe_min_pairs = 2000000000LL;
+  // Constant-bank path: when coincident pairs exist, let the probe also mark WHICH (chunk, target block) pairs hold
+  // them, so every other CTA still takes the unmasked loop (targets == sources: one coincident pair per target).
+  int64_t probe_per_block = 1;
 };
 
 struct Global {
@@ -271,22 +274,25 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
 // device, stream ordered) and launch eval_pairs_const_kernel over all targets.  Each launch costs a fixed ~20 us
 // (kernel boundary + cold constant cache), so the path is used only when a chunk x Nt is >= ~2 ms of work.
 
+template <class Real> int const_banks_wanted() {
+  return (int)std::max<int64_t>(1, std::min<int64_t>(sizeof(Real) == 8 ? g.opt.const_banks : g.opt.const_banks_fp32, CONST_MAX_BANKS));
+}
+template <class Real> int64_t const_target_blocks(int64_t Nt) {
+  using Tn = Tune<Real>;
+  return (Nt + Tn::CONST_NT * Tn::CONST_T - 1) / (Tn::CONST_NT * Tn::CONST_T);
+}
+
+// `stage`: the packed sources in chunk segments (ConstGeom); `flags`: the probe's two ints, or nullptr when it did not run
 template <class Real, int KID, int RSQ>
-int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Real* r_trg, Real* v_trg, const int* must_mask, Real ctx0, cudaStream_t stream) {
+int launch_eval_const(int dev, const ConstGeom& cg, bool use_bits, int64_t Ns, int64_t Nt, const Real* stage, const Real* r_trg, Real* v_trg, const int* flags, Real ctx0, cudaStream_t stream) {
   using Tn = Tune<Real>;
   constexpr int T = Tn::CONST_T, NT = Tn::CONST_NT;
-  constexpr int REC = RecTraits<Real, KID>::REC;
   constexpr int K1 = KerTraits<KID>::K1;
   auto kern = eval_pairs_const_kernel<Real, KID, T, NT, RSQ, Tn::CONST_U, Tn::CONST_MINB>;
-  const int64_t n_tb = (Nt + NT * T - 1) / (NT * T);
+  const int64_t n_tb = const_target_blocks<Real>(Nt);
   if (n_tb > 2147483647LL) return fail("too many target blocks");
   DeviceInfo& di = g.dev[dev];
-  // Banks: chunk i streams through slice i % banks of the constant buffer on its own stream (eval_const_kernel.cuh).
-  int banks = (int)std::max<int64_t>(1, std::min<int64_t>(sizeof(Real) == 8 ? g.opt.const_banks : g.opt.const_banks_fp32, CONST_MAX_BANKS));
-  const int CH = const_bank_records<Real, KID>(banks);
-  if ((Ns + CH - 1) / CH < 2 * banks) banks = 1;  // too few chunks to pipeline
-  const int CHB = const_bank_records<Real, KID>(banks);
-  const int bank_stride = (CONST_PACK_BYTES / banks / 16 * 16) / (int)sizeof(Real);
+  const int banks = cg.banks;
   // Cluster split of a chunk along grid.y when target blocks alone cannot fill the SMs.  With one bank every launch
   // stands alone and wants several CTAs per SM; with overlapping launches one CTA slot's worth per SM is enough.
   const int64_t want_ctas = (banks > 1 ? g.opt.const_ctas_per_sm_overlap : g.opt.const_ctas_per_sm) * (int64_t)di.sms;
@@ -295,7 +301,7 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   ConstEvalArgs<Real> a = {};
   a.r_trg = r_trg;
   a.Nt = Nt;
-  a.allow_unmasked = must_mask != nullptr;
+  a.allow_unmasked = flags != nullptr;
   a.ctx0 = ctx0;
   a.scale = scale_factor<Real>(KID);
   cudaLaunchConfig_t cfg = {};
@@ -320,7 +326,7 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
   } else {
     CU_TRY(cudaStreamWaitEvent(stream, di.const_done, 0));  // the previous user of the constant bank, on any stream
   }
-  if (must_mask) CU_TRY(cudaMemcpyToSymbolAsync(c_eval_must_mask, must_mask, sizeof(int), 0, cudaMemcpyDeviceToDevice, stream));
+  if (flags) CU_TRY(cudaMemcpyToSymbolAsync(c_eval_must_mask, flags, 2 * sizeof(int), 0, cudaMemcpyDeviceToDevice, stream));
   // banks 1.. accumulate into their own zeroed buffers (launches of different banks overlap and must not race on v_trg)
   Real* alt = nullptr;
   const size_t nv = (size_t)Nt * K1;
@@ -331,18 +337,21 @@ int launch_eval_const(int dev, int64_t Ns, int64_t Nt, const Real* pack, const R
     for (int b = 1; b < banks; b++) CU_TRY(cudaStreamWaitEvent(di.bank_stream[b], di.const_fork, 0));
   }
   int launches = 0;
-  int64_t i = 0;
-  for (int64_t s0 = 0; s0 < Ns; s0 += CHB, i++) {
+  const int64_t seg_reals = cg.seg_bytes / (int64_t)sizeof(Real);
+  for (int64_t i = 0; i < cg.n_chunks; i++) {
     const int b = (int)(i % banks);
     cudaStream_t st = b ? di.bank_stream[b] : stream;
-    const int n = (int)std::min<int64_t>(CHB, Ns - s0);
-    CU_TRY(cudaMemcpyToSymbolAsync(c_src_pack, pack + s0 * REC, sizeof(Real) * (size_t)n * REC, sizeof(Real) * (size_t)b * bank_stride, cudaMemcpyDeviceToDevice, st));
+    const int n = (int)std::min<int64_t>(cg.chunk, Ns - i * cg.chunk);
+    // one copy per launch: the chunk's records and, behind them, its coincidence bits
+    const size_t bytes = use_bits ? (size_t)cg.seg_bytes : (size_t)n * cg.rec_bytes;
+    CU_TRY(cudaMemcpyToSymbolAsync(c_src_pack, stage + i * seg_reals, bytes, (size_t)b * cg.bank_stride, cudaMemcpyDeviceToDevice, st));
     a.v_trg = b ? alt + (size_t)(b - 1) * nv : v_trg;
     a.n_rec = n;
     a.sub_len = (n + cl - 1) / cl;
     a.full_ranks = n / a.sub_len;
     a.tail_len = n % a.sub_len;
-    a.bank_off = b * bank_stride;
+    a.bank_off = b * (cg.bank_stride / (int)sizeof(Real));
+    a.bits_off = use_bits ? (b * cg.bank_stride + cg.chunk * cg.rec_bytes) / 4 : -1;
     cfg.stream = st;
     CU_TRY(cudaLaunchKernelEx(&cfg, kern, a));
     launches++;
@@ -373,38 +382,62 @@ template <class Real, int KID, int RSQ>
 int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, Real ctx0, cudaStream_t stream) {
   using Tn = Tune<Real>;
   constexpr int REC = RecTraits<Real, KID>::REC;
+  const bool fp32_const = g.opt.const_fp32 == 1 || (g.opt.const_fp32 < 0 && Nt >= (1 << 17) && KID != LAPLACE3D_FXU);
+  const bool use_const = Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || fp32_const);
+  // coincidence probe (big problems only): lets the pair kernels skip the r2 == 0 mask where it cannot matter
+  const bool probe = g.opt.probe_min_pairs > 0 && (double)Ns * (double)Nt >= (double)g.opt.probe_min_pairs;
+  ConstGeom cg = {};
+  // the bit rows are part of the layout whether or not this call fills them: the chunk length, and with it the summation
+  // order, must not depend on the probe options (masked and probed runs are bit-identical)
+  if (use_const) cg = const_geometry<Real, KID>(Ns, const_target_blocks<Real>(Nt), const_banks_wanted<Real>(), true);
+  const bool use_bits = use_const && cg.row_words && probe && g.opt.probe_per_block != 0;
+  // packed sources: contiguous records, or chunk segments (records + coincidence bits) for the constant-bank path
+  const size_t pack_bytes = use_const ? (size_t)cg.n_chunks * cg.seg_bytes : sizeof(Real) * (size_t)Ns * REC;
   Real* pack = nullptr;
-  CU_TRY(cudaMallocAsync((void**)&pack, sizeof(Real) * (size_t)Ns * REC, stream));
+  CU_TRY(cudaMallocAsync((void**)&pack, pack_bytes, stream));
+  if (use_bits) CU_TRY(cudaMemsetAsync(pack, 0, pack_bytes, stream));  // the bit rows start clear
   {
     const int blocks = (int)std::min<int64_t>((Ns + 255) / 256, 8192);
-    pack_sources_kernel<Real, KID><<<blocks, 256, 0, stream>>>(Ns, r_src, n_src, v_src, pack);
+    const int64_t chunk_len = use_const ? cg.chunk : std::max<int64_t>(Ns, 1);
+    pack_sources_kernel<Real, KID><<<blocks, 256, 0, stream>>>(Ns, r_src, n_src, v_src, pack, chunk_len, use_const ? cg.seg_bytes / (int64_t)sizeof(Real) : 0);
     CU_TRY(cudaGetLastError());
   }
-  // coincidence probe (big problems only): lets the pair kernels skip the r2 == 0 mask when it cannot matter
-  int* must_mask = nullptr;
+  int* flags = nullptr;
   unsigned long long* table = nullptr;
   int n_probe_launches = 0;
-  if (g.opt.probe_min_pairs > 0 && (double)Ns * (double)Nt >= (double)g.opt.probe_min_pairs) {
+  if (probe) {
     uint64_t slots = 1024;
     while (slots < 2 * (uint64_t)Ns) slots <<= 1;
-    CU_TRY(cudaMallocAsync((void**)&table, (slots + 2) * sizeof(unsigned long long), stream));
-    CU_TRY(cudaMemsetAsync(table, 0, (slots + 2) * sizeof(unsigned long long), stream));
-    must_mask = reinterpret_cast<int*>(table + slots);
-    coincidence_insert_kernel<Real><<<(int)std::min<int64_t>((Ns + 255) / 256, 4096), 256, 0, stream>>>(Ns, r_src, table, slots - 1);
-    coincidence_probe_kernel<Real><<<(int)std::min<int64_t>((Nt + 255) / 256, 4096), 256, 0, stream>>>(Nt, r_trg, table, slots - 1, must_mask);
+    const bool bits = use_bits;
+    // [slots keys | 2 flags (one 64-bit word) | pad] [cmin | cmax]
+    const size_t key_bytes = (slots + 2) * sizeof(unsigned long long);
+    CU_TRY(cudaMallocAsync((void**)&table, key_bytes + (bits ? 2 * slots * sizeof(unsigned) : 0), stream));
+    CU_TRY(cudaMemsetAsync(table, 0, key_bytes + (bits ? 2 * slots * sizeof(unsigned) : 0), stream));
+    flags = reinterpret_cast<int*>(table + slots);
+    CoincidenceBits cb = {};
+    if (bits) {
+      cb.cmin = reinterpret_cast<unsigned*>(table + slots + 2);
+      cb.cmax = cb.cmin + slots;
+      CU_TRY(cudaMemsetAsync(cb.cmin, 0xFF, slots * sizeof(unsigned), stream));
+      cb.bits = reinterpret_cast<unsigned*>(pack) + (int64_t)cg.chunk * cg.rec_bytes / 4;
+      cb.row_stride = cg.seg_bytes / 4;
+      cb.chunk_len = cg.chunk;
+      cb.trg_per_blk = Tn::CONST_NT * Tn::CONST_T;
+    }
+    coincidence_insert_kernel<Real><<<(int)std::min<int64_t>((Ns + 255) / 256, 4096), 256, 0, stream>>>(Ns, r_src, table, slots - 1, cb);
+    coincidence_probe_kernel<Real><<<(int)std::min<int64_t>((Nt + 255) / 256, 4096), 256, 0, stream>>>(Nt, r_trg, table, slots - 1, flags, cb);
     CU_TRY(cudaGetLastError());
     n_probe_launches = 2;
   }
   int rc;
-  const bool fp32_const = g.opt.const_fp32 == 1 || (g.opt.const_fp32 < 0 && Nt >= (1 << 17) && KID != LAPLACE3D_FXU);
-  if (Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || fp32_const))
-    rc = launch_eval_const<Real, KID, RSQ>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream);
+  if (use_const)
+    rc = launch_eval_const<Real, KID, RSQ>(dev, cg, use_bits, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream);
   else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8 && KerTraits<KID>::K1 <= 4)  // 9 accumulators x 4 targets would spill
-    rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream, 8 * Tn::WIDE_TILE, 64);
+    rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, 8 * Tn::WIDE_TILE, 64);
   else if (Nt <= g.opt.few_max_targets)
-    rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream, Tn::FEW_TILE, 1024);
+    rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, Tn::FEW_TILE, 1024);
   else
-    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, must_mask, ctx0, stream, 8 * Tn::TILE, 64);
+    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, 8 * Tn::TILE, 64);
   if (table) cudaFreeAsync(table, stream);
   tl.n_launches += n_probe_launches;
   if (rc) {
@@ -958,6 +991,7 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "const_ctas_per_sm")) g.opt.const_ctas_per_sm = value;
   else if (!strcmp(name, "const_ctas_per_sm_overlap")) g.opt.const_ctas_per_sm_overlap = value;
   else if (!strcmp(name, "probe_min_pairs")) g.opt.probe_min_pairs = value;
+  else if (!strcmp(name, "probe_per_block")) g.opt.probe_per_block = value;
   else return fail("unknown option '%s'", name);
   return 0;
 }

@@ -179,3 +179,30 @@ def test_torus_surface_self_evaluation(sb, cpu_oracle):
     u_in = sb.Laplace3D_DxU.Eval(None, inside, X, Nrm, w)
     u_out = sb.Laplace3D_DxU.Eval(None, outside, X, Nrm, w)
     assert np.allclose(np.abs(u_in), 1.0, atol=1e-6) and np.allclose(u_out, 0.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("kernel,dtype", [("Stokes3D_FxU", np.float64), ("Laplace3D_DxU", np.float64), ("Stokes3D_DxU", np.float32)])
+def test_self_interaction_per_block_unmasking(sb, cpu_oracle, kernel, dtype):
+    """targets == sources on the constant-bank path: every target has exactly one r2 == 0 pair, so the global verdict of
+    the coincidence probe is "mask", but only the (chunk, target block) pairs on the diagonal hold such pairs; every other
+    CTA runs the unmasked loop.  Must equal the fully masked run bit for bit and match the reference."""
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    N = 70001
+    r_src, n_src, v_src, _ = synth.cube(N, 0, k0, nd, dtype=dtype)
+    K = sb.KERNELS[kernel]
+    try:
+        sb.set_option("const_fp32", 1)
+        sb.set_option("probe_min_pairs", 1)
+        got = K.Eval(None, r_src, r_src, n_src, v_src, dtype=dtype)
+        assert sb.last_plan()["threads"] in (128, 256) and sb.last_plan()["n_launches"] > 20  # the constant-bank path
+        sb.set_option("probe_per_block", 0)
+        glob = K.Eval(None, r_src, r_src, n_src, v_src, dtype=dtype)
+        sb.set_option("probe_min_pairs", 0)
+        masked = K.Eval(None, r_src, r_src, n_src, v_src, dtype=dtype)
+    finally:
+        sb.reset_options()
+    assert np.all(np.isfinite(got)) and np.array_equal(got, masked) and np.array_equal(glob, masked)
+    idx = np.arange(256) * (N // 256)
+    want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_src.reshape(-1, 3)[idx].reshape(-1), dtype=np.float64 if dtype == np.float32 else dtype)
+    assert rel_err(got.reshape(-1, k1)[idx].reshape(-1), want) <= (1e-12 if dtype == np.float64 else 1e-5)

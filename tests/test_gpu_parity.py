@@ -251,40 +251,47 @@ def test_every_eval_path_agrees(sb, cpu_oracle, kernel, dtype):
         sb.reset_options()
 
 
+@pytest.mark.parametrize("path", ["ring", "const", "const_global_flag"])
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("kernel", ["Stokes3D_FxU", "Laplace3D_FxU", "Stokes3D_DxU"])
-def test_coincidence_probe_keeps_the_mask_when_needed(sb, cpu_oracle, kernel, dtype):
-    """The O(Ns+Nt) coincidence probe lets the kernels drop the r2 == 0 mask only when no source/target pair can need
-    it.  Forced on at small sizes: (a) disjoint sets -> unmasked loop, bit-identical to the masked one; (b) ONE
-    coincident pair hidden among thousands; (c) targets == sources; (d) distinct points closer than sqrt(DBL_MIN)
-    (r2 underflows); every case must match the oracle and contain no Inf/NaN."""
+def test_coincidence_probe_keeps_the_mask_when_needed(sb, cpu_oracle, kernel, dtype, path):
+    """The O(Ns+Nt) coincidence probe lets the kernels drop the r2 == 0 mask only where no source/target pair can need
+    it: globally (ring path), or per (chunk, target block) on the constant-bank path.  Forced on at small sizes:
+    (a) disjoint sets -> unmasked loop, bit-identical to the masked one; (b) ONE coincident pair hidden among thousands;
+    (c) targets == sources (one coincident pair per target, spread over every chunk and block); (d) a source point
+    duplicated into more chunks than the refinement tracks (it must give up, not miss one); (e) distinct points closer
+    than sqrt(DBL_MIN) (r2 underflows); every case must match the oracle and contain no Inf/NaN."""
     from sctl_b200 import synth
     K = sb.KERNELS[kernel]
     k0, k1, nd = cases.KERNELS[kernel]
-    Ns, Nt = 5000, 4100
+    Ns, Nt = 9000, 4100
     r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
     tiny = 1e-160 if dtype == np.float64 else 1e-30
-    variants = {"disjoint": r_trg.copy()}
-    one = r_trg.copy(); one[3 * 1234:3 * 1234 + 3] = r_src[3 * 4321:3 * 4321 + 3]; variants["one_pair"] = one
-    variants["self"] = r_src[: Nt * 3].copy()
+    variants = {"disjoint": (r_src, r_trg.copy())}
+    one = r_trg.copy(); one[3 * 1234:3 * 1234 + 3] = r_src[3 * 4321:3 * 4321 + 3]; variants["one_pair"] = (r_src, one)
+    variants["self"] = (r_src, r_src[: Nt * 3].copy())
+    dup = r_src.copy()
+    for j in range(0, Ns, 450):  # 20 copies of one point, 450 sources apart: more chunks than MAX_CHUNK_SPAN
+        dup[3 * j:3 * j + 3] = r_trg[3 * 77:3 * 77 + 3]
+    variants["spread_duplicates"] = (dup, r_trg.copy())
     und_s, und_t = r_src.copy(), r_trg.copy()
     und_s[3 * 77:3 * 77 + 3] = [0.0, tiny, -tiny]; und_t[3 * 99:3 * 99 + 3] = [tiny, 0.0, 2 * tiny]  # distinct, r2 underflows to 0
+    variants["underflow"] = (und_s, und_t)
+    opts = {"ring": {}, "const": dict(const_min_targets=1, const_fp32=1), "const_global_flag": dict(const_min_targets=1, const_fp32=1, probe_per_block=0)}[path]
     try:
-        for name, trg in variants.items():
-            src = und_s if name == "underflow" else r_src
-            want = cpu_oracle.eval(kernel, src, n_src, v_src, trg, dtype=dtype)
+        for name, (src, trg) in variants.items():
+            sb.reset_options()
+            for k, v in opts.items():
+                sb.set_option(k, v)
             sb.set_option("probe_min_pairs", 0)
             masked = K.Eval(None, trg, src, n_src, v_src, dtype=dtype)
             sb.set_option("probe_min_pairs", 1)
             probed = K.Eval(None, trg, src, n_src, v_src, dtype=dtype)
             assert np.all(np.isfinite(probed)), name
             assert np.array_equal(masked, probed), name  # same arithmetic on every pair that is not masked
-            assert rel_err(probed, want) <= TOL[dtype], (name, rel_err(probed, want))
-        sb.set_option("probe_min_pairs", 1)
-        got = K.Eval(None, und_t, und_s, n_src, v_src, dtype=dtype)
-        sb.set_option("probe_min_pairs", 0)
-        ref = K.Eval(None, und_t, und_s, n_src, v_src, dtype=dtype)
-        assert np.all(np.isfinite(got)) and np.array_equal(got, ref)
+            if name != "underflow":  # the reference itself overflows there (r2 underflows to 0 for distinct points)
+                want = cpu_oracle.eval(kernel, src, n_src, v_src, trg, dtype=dtype)
+                assert rel_err(probed, want) <= TOL[dtype], (name, rel_err(probed, want))
     finally:
         sb.reset_options()
 

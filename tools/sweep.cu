@@ -307,7 +307,7 @@ template <class Real, int KID> void setup(Ctx& c, int64_t Ns, int64_t Nt) {
   fill_kernel<Real><<<1024, 256>>>((Real*)c.r_trg, Nt * 3, 2, (Real)0);
   fill_kernel<Real><<<1024, 256>>>((Real*)c.n_src, Ns * 3, 3, (Real)-0.5);
   fill_kernel<Real><<<1024, 256>>>((Real*)c.v_src, Ns * K0, 4, (Real)-0.5);
-  pack_sources_kernel<Real, KID><<<1024, 256>>>(Ns, (const Real*)c.r_src, (const Real*)c.n_src, (const Real*)c.v_src, (Real*)c.pack);
+  pack_sources_kernel<Real, KID><<<1024, 256>>>(Ns, (const Real*)c.r_src, (const Real*)c.n_src, (const Real*)c.v_src, (Real*)c.pack, (int64_t)Ns, (int64_t)0);
   CK(cudaDeviceSynchronize());
 }
 void teardown(Ctx& c) {
