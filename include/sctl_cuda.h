@@ -176,8 +176,10 @@ int sctl_cuda_near_apply(sctl_cuda_near_t h, const void* F, int64_t nF, void* U,
  *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64;
  *                       FP32 per "const_fp32": 0 never, 1 always, -1 (default) for Nt >= 2^17 and every kernel but
  *                       Laplace3D_FxU, where it measured faster than the shared-memory ring);
- *   "wide_min_targets"  (default 2^16): at or above (FP64), 4 targets per thread, one CTA per SM;
+ *   "wide_min_targets"  (default 2^13): at or above (FP64), 4 targets per thread, one CTA per SM;
  *   "few_max_targets"   (default 2048): at or below, the warps of a CTA share 32 targets and split the sources.
+ *   "ring_min_tiles" / "ring_max_split" (defaults 1 / 64): shared-memory ring paths: shortest source chunk (in tiles) and
+ *                       most chunks the grid planner may use when it splits the sources to fill the SMs;
  *   "const_banks" / "const_banks_fp32" (defaults 2 / 4): slices of the constant buffer in flight on the constant-bank
  *                       path (FP64 / FP32); chunk i streams through slice i % banks on its own stream so consecutive
  *                       launches overlap (1..4);

@@ -56,6 +56,9 @@ constexpr int MAX_DEV = 16;
 struct ThreadState {
   cudaStream_t stream[MAX_DEV] = {};
   cudaEvent_t ev[MAX_DEV][4] = {};
+  // small-call arena: one pinned host buffer and one device buffer per (thread, device), see eval_host_small()
+  char* arena_h[MAX_DEV] = {};
+  char* arena_d[MAX_DEV] = {};
   double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
   int grid_x = 0, grid_y = 0, threads = 0, smem = 0, ctas_per_sm = 0, n_launches = 0;
   double wave_eff = 0;
@@ -96,7 +99,10 @@ struct Options {
   //   otherwise               : shared-memory ring, 2 targets per thread, two CTAs per SM
   int64_t const_min_targets = 1 << 15;
   int64_t few_max_targets = 2048;
-  int64_t wide_min_targets = 1 << 16;
+  // shared-memory ring: shortest source chunk (in tiles) the grid planner may give a CTA when it splits the sources
+  int64_t ring_min_tiles = 1;
+  int64_t ring_max_split = 64;
+  int64_t wide_min_targets = 1 << 13;
   // Constant-bank path: slices of the buffer in flight (1 = one launch at a time), and the CTAs per SM a launch should
   // have before its chunk is split across a cluster (stand-alone launches / overlapping launches).
   int64_t const_banks = 2;
@@ -113,6 +119,8 @@ struct Options {
   // Constant-bank path: when coincident pairs exist, let the probe also mark WHICH (chunk, target block) pairs hold
   // them, so every other CTA still takes the unmasked loop (targets == sources: one coincident pair per target).
   int64_t probe_per_block = 1;
+  // host-pointer calls whose arrays fit 1 MB go through a per-thread pinned/device arena (one upload, one download)
+  int64_t small_call_arena = 1;
 };
 
 struct Global {
@@ -433,11 +441,11 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
   if (use_const)
     rc = launch_eval_const<Real, KID, RSQ>(dev, cg, use_bits, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream);
   else if (Nt >= g.opt.wide_min_targets && sizeof(Real) == 8 && KerTraits<KID>::K1 <= 4)  // 9 accumulators x 4 targets would spill
-    rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, 8 * Tn::WIDE_TILE, 64);
+    rc = launch_eval_cfg<Real, KID, (KerTraits<KID>::K1 <= 4 ? Tn::WIDE_T : Tn::T), Tn::WIDE_NW, 1, RSQ, Tn::WIDE_TILE, Tn::WIDE_STAGES, Tn::WIDE_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, (int)g.opt.ring_min_tiles * Tn::WIDE_TILE, (int)g.opt.ring_max_split);
   else if (Nt <= g.opt.few_max_targets)
     rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, Tn::FEW_TILE, 1024);
   else
-    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, 8 * Tn::TILE, 64);
+    rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, (int)g.opt.ring_min_tiles * Tn::TILE, (int)g.opt.ring_max_split);
   if (table) cudaFreeAsync(table, stream);
   tl.n_launches += n_probe_launches;
   if (rc) {
@@ -650,6 +658,56 @@ struct DevBuf {
     if (p) cudaFreeAsync(p, st);
   }
 };
+
+// Small calls (all arrays together below SMALL_ARENA bytes) are latency-bound: five pageable uploads, five pool
+// allocations and a pageable download cost more than the kernel.  They go through a per-thread arena instead: the inputs
+// are gathered into ONE pinned buffer, uploaded with one copy into a persistent device buffer, and the result comes back
+// through the same pinned buffer.  (BoundaryIntegralOp's near-field setup and FMM leaf interactions issue thousands of
+// such calls, many of them concurrently from OpenMP threads: boundary_integral.txx:1169-1211.)
+constexpr size_t SMALL_ARENA = 1 << 20;
+inline size_t arena_align(size_t n) { return (n + 255) & ~(size_t)255; }
+
+int ensure_arena(int dev) {
+  if (tl.arena_h[dev]) return 0;
+  CU_TRY(cudaHostAlloc((void**)&tl.arena_h[dev], SMALL_ARENA, cudaHostAllocDefault));
+  CU_TRY(cudaMalloc((void**)&tl.arena_d[dev], SMALL_ARENA));
+  return 0;
+}
+
+int eval_host_small(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const char* r_src, const char* n_src, const char* v_src, const char* r_trg,
+                    char* v_trg, double ctx0) {
+  const KernelInfo ki = kernel_info(kid);
+  const size_t rb = (size_t)real_bytes;
+  const size_t b_rs = rb * Ns * 3, b_vs = rb * Ns * ki.k0, b_ns = ki.nd ? rb * Ns * ki.nd : 0, b_rt = rb * Nt * 3, b_vt = rb * Nt * ki.k1;
+  const size_t o_vt = 0, o_rs = o_vt + arena_align(b_vt), o_vs = o_rs + arena_align(b_rs), o_ns = o_vs + arena_align(b_vs), o_rt = o_ns + arena_align(b_ns);
+  const size_t total = o_rt + arena_align(b_rt);
+  CU_TRY(cudaSetDevice(dev));
+  if (ensure_device(dev) || ensure_arena(dev)) return 1;
+  cudaStream_t st = tl.stream[dev];
+  char *h = tl.arena_h[dev], *d = tl.arena_d[dev];
+  memcpy(h + o_vt, v_trg, b_vt);
+  memcpy(h + o_rs, r_src, b_rs);
+  memcpy(h + o_vs, v_src, b_vs);
+  if (b_ns) memcpy(h + o_ns, n_src, b_ns);
+  memcpy(h + o_rt, r_trg, b_rt);
+  CU_TRY(cudaEventRecord(tl.ev[dev][0], st));
+  CU_TRY(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaEventRecord(tl.ev[dev][1], st));
+  if (eval_device_any(dev, kid, real_bytes, digits, Ns, Nt, d + o_rs, b_ns ? d + o_ns : nullptr, d + o_vs, d + o_rt, d + o_vt, ctx0, st)) return 1;
+  CU_TRY(cudaEventRecord(tl.ev[dev][2], st));
+  CU_TRY(cudaMemcpyAsync(h + o_vt, d + o_vt, b_vt, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaEventRecord(tl.ev[dev][3], st));
+  CU_TRY(cudaStreamSynchronize(st));
+  memcpy(v_trg, h + o_vt, b_vt);
+  float a = 0, b = 0, c = 0;
+  CU_TRY(cudaEventElapsedTime(&a, tl.ev[dev][0], tl.ev[dev][1]));
+  CU_TRY(cudaEventElapsedTime(&b, tl.ev[dev][1], tl.ev[dev][2]));
+  CU_TRY(cudaEventElapsedTime(&c, tl.ev[dev][2], tl.ev[dev][3]));
+  tl.h2d_ms = a;
+  tl.kernel_ms = b;
+  tl.d2h_ms = c;
+  return 0;
+}
 
 // One GPU: upload everything, run, download the target range [t0, t1).
 int eval_host_one(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t t0, int64_t t1, const char* r_src, const char* n_src, const char* v_src,
@@ -909,6 +967,12 @@ int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_
     }
     return 0;
   }
+  {
+    const size_t rb = (size_t)real_bytes;
+    const size_t total = arena_align(rb * Nt * ki.k1) + arena_align(rb * Ns * 3) + arena_align(rb * Ns * ki.k0) + arena_align(rb * Ns * ki.nd) + arena_align(rb * Nt * 3);
+    if (total <= SMALL_ARENA && g.opt.small_call_arena)
+      return eval_host_small(dev, kernel_id, real_bytes, digits, Ns, Nt, (const char*)r_src, (const char*)n_src, (const char*)v_src, (const char*)r_trg, (char*)v_trg, ctx0);
+  }
   return eval_host_one(dev, kernel_id, real_bytes, digits, Ns, 0, Nt, (const char*)r_src, (const char*)n_src, (const char*)v_src, (const char*)r_trg,
                        (char*)v_trg, ctx0, true);
 }
@@ -928,6 +992,25 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
   const int64_t rows = Ns * ki.k0, cols = Nt * ki.k1;
   if (ldM < cols) return fail("ldM (%lld) smaller than Nt*K1 (%lld)", (long long)ldM, (long long)cols);
   cudaStream_t st = tl.stream[dev];
+  {  // small-call arena (see eval_host_small): one pinned upload, one pinned download, no pool allocations
+    const size_t b_rs = rb * Ns * 3, b_ns = ki.nd ? rb * Ns * ki.nd : 0, b_rt = rb * Nt * 3, b_M = rb * rows * cols;
+    const size_t o_rs = 0, o_ns = o_rs + arena_align(b_rs), o_rt = o_ns + arena_align(b_ns), o_M = o_rt + arena_align(b_rt);
+    if (o_M + arena_align(b_M) <= SMALL_ARENA && g.opt.small_call_arena) {
+      if (ensure_arena(dev)) return 1;
+      char *h = tl.arena_h[dev], *d = tl.arena_d[dev];
+      memcpy(h + o_rs, r_src, b_rs);
+      if (b_ns) memcpy(h + o_ns, n_src, b_ns);
+      memcpy(h + o_rt, r_trg, b_rt);
+      CU_TRY(cudaMemcpyAsync(d, h, o_M, cudaMemcpyHostToDevice, st));
+      if (kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d + o_rs, b_ns ? d + o_ns : nullptr, d + o_rt, d + o_M, cols, ctx0, st)) return 1;
+      CU_TRY(cudaMemcpyAsync(h + o_M, d + o_M, b_M, cudaMemcpyDeviceToHost, st));
+      CU_TRY(cudaStreamSynchronize(st));
+      if (ldM == cols) memcpy(M, h + o_M, b_M);
+      else
+        for (int64_t r = 0; r < rows; r++) memcpy((char*)M + rb * ldM * r, h + o_M + rb * cols * r, rb * cols);
+      return 0;
+    }
+  }
   DevBuf d_rs, d_ns, d_rt, d_M;
   if (d_rs.alloc(rb * Ns * 3, st) || d_rt.alloc(rb * Nt * 3, st) || d_M.alloc(rb * rows * cols, st)) return 1;
   if (ki.nd && d_ns.alloc(rb * Ns * ki.nd, st)) return 1;
@@ -984,6 +1067,8 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   std::lock_guard<std::mutex> lk(g.mu);
   if (!strcmp(name, "const_min_targets")) g.opt.const_min_targets = value;
   else if (!strcmp(name, "few_max_targets")) g.opt.few_max_targets = value;
+  else if (!strcmp(name, "ring_min_tiles")) g.opt.ring_min_tiles = std::max<int64_t>(1, value);
+  else if (!strcmp(name, "ring_max_split")) g.opt.ring_max_split = std::max<int64_t>(1, std::min<int64_t>(value, 1024));
   else if (!strcmp(name, "wide_min_targets")) g.opt.wide_min_targets = value;
   else if (!strcmp(name, "const_fp32")) g.opt.const_fp32 = value;
   else if (!strcmp(name, "const_banks")) g.opt.const_banks = value;
@@ -992,6 +1077,7 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   else if (!strcmp(name, "const_ctas_per_sm_overlap")) g.opt.const_ctas_per_sm_overlap = value;
   else if (!strcmp(name, "probe_min_pairs")) g.opt.probe_min_pairs = value;
   else if (!strcmp(name, "probe_per_block")) g.opt.probe_per_block = value;
+  else if (!strcmp(name, "small_call_arena")) g.opt.small_call_arena = value;
   else return fail("unknown option '%s'", name);
   return 0;
 }
