@@ -320,6 +320,15 @@ def main():
         line["parity"] = {"max_abs_err_over_vinf": float(np.abs(got.astype(np.float64) - cpu_res.astype(np.float64)).max() / np.abs(full.cpu().numpy()).max()),
                           "gate": 1e-12 if rb == 8 else "1e-5 for Ns <= 2^14; beyond that two FP32 summation orders differ by more (SURVEY 7.3)",
                           "checked": "%d strided targets x all sources vs the CPU arm above" % nsub}
+    if world > 1 and not args.no_cpu_baseline:
+        # multi-GPU runs carry no cpu_baseline (N = 1 only) but still check the gathered result against the CPU reference
+        nsub = min(N, 1 << 12)
+        torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))  # torchrun pins OMP_NUM_THREADS=1; the checker shares the OpenMP runtime
+        _, info, (idx, cpu_res), _ = cpu_arm(kernel, N, nsub, 1, 1, want_result=True, dtype=npdt, points=args.points, log2n=args.log2n)
+        got = full.cpu().numpy().reshape(-1, k1)[idx].reshape(-1)
+        line["parity"] = {"max_abs_err_over_vinf": float(np.abs(got.astype(np.float64) - cpu_res.astype(np.float64)).max() / np.abs(full.cpu().numpy()).max()),
+                          "gate": 1e-12 if rb == 8 else "1e-5 for Ns <= 2^14; beyond that two FP32 summation orders differ by more (SURVEY 7.3)",
+                          "checked": "%d strided targets x all sources of the gathered %d-GPU result vs the reference CPU Eval (%s, %d threads)" % (nsub, world, info["kind"], info["cores"])}
     out.write(json.dumps(line) + "\n")
     out.flush()
     if world > 1:

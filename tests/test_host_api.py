@@ -85,6 +85,12 @@ def test_compute_fails_loudly_without_gpu(sbm):
         sbm.init(1)
     with pytest.raises(sbm.SctlCudaError):
         sbm.fma_peak(8, 1.0)
+    # the session layers have no CPU fallback either
+    with pytest.raises(sbm.SctlCudaError, match="no CUDA device"):
+        sbm.ParticleDirect(np.float64)
+    one = np.array([1], dtype=np.int64)
+    with pytest.raises(sbm.SctlCudaError, match="no CUDA device"):
+        sbm.NearBlocks(sbm.Laplace3D_FxU, one * 0, one * 0, one, one * 0, one, one * 0)
 
 
 def test_precondition_violations_raise(sbm):
