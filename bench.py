@@ -292,7 +292,7 @@ def main():
     # (profiles/r1_ncu_eval_const_2banks_stokes_fxu_f64.md): 50.38 MB read + 0.02 MB written per constant-bank launch at 2^20
     # targets (r_trg + the v_trg read-modify-write; the write-back stays in L2); null for any other workload
     traffic = 50.40e6 if (kernel, args.log2n, rb, world) == ("Stokes3D_FxU", 20, 8, 1) else None
-    const_path = plan["threads"] == 256 and plan["n_launches"] > 10
+    const_path = plan["n_launches"] > 10  # one launch per source chunk (the ring paths need at most 5)
     # launches of one Eval on the constant-bank path: pack + 2 probe kernels + one pair kernel per chunk + the bank combine
     pair_launches = max(1, plan["n_launches"] - 4) if const_path else 1
     roofline = {"bound": "fp64" if rb == 8 else "fp32", "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": traffic,
