@@ -185,6 +185,10 @@ int sctl_cuda_near_apply(sctl_cuda_near_t h, const void* F, int64_t nF, void* U,
  *                       launches overlap (1..4);
  *   "const_ctas_per_sm" / "const_ctas_per_sm_overlap" (defaults 6 / 1): CTAs per SM a launch should have before its
  *                       chunk is split across a thread-block cluster (one launch at a time / overlapping launches);
+ *   "small_call_arena"  (default 1): host-pointer calls whose arrays fit 1 MB use a per-thread pinned/device arena
+ *                       (one upload, one download, no pool allocations);
+ *   "probe_per_block"   (default 1): on the constant-bank path the coincidence check also records which (source chunk,
+ *                       target block) pairs hold coincident points, so only those CTAs keep the mask;
  *   "probe_min_pairs"   (default 2e9): at or above Ns*Nt, Eval first checks (O(Ns+Nt), on the device) whether any source
  *                       and target (nearly) coincide and lets the pair kernels drop the r^2 == 0 mask when none do;
  *                       <= 0 disables the check.  Results are bit-identical either way.

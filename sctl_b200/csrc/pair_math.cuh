@@ -292,8 +292,73 @@ template <class Real> struct PairApply<BIOTSAVART3D_FXDU, Real> {
 };
 
 // ---- Helmholtz kernels (kernel_functions.hpp:490-659): G = exp(i mu r) / r and derivatives; record = [x y z f_re f_im (n)] ----
-__device__ __forceinline__ void sincos_real(double x, double* s, double* c) { sincos(x, s, c); }
-__device__ __forceinline__ void sincos_real(float x, float* s, float* c) { sincosf(x, s, c); }
+// FP64 sin and cos of the same argument.  CUDA's sincos() spends ~21 FP64 and ~45 auxiliary instructions per call in
+// these loops (conversions on the XU pipe, a slow-path call, coefficient moves); next to a saturated FP64 pipe the
+// auxiliary ones cost almost as much as the arithmetic (profiles/r1_whatif_and_aux_cost.txt).  This version keeps the
+// arithmetic -- round-to-nearest quadrant by the 1.5*2^52 trick, two-term Cody-Waite reduction with FMA, the fdlibm
+// minimax polynomials on [-pi/4, pi/4] -- takes its coefficients straight from the constant bank, and selects the
+// quadrant with integer ops on the high words.  Max abs error 1.3e-16 for |x| <= 1e5 (checked against long double on
+// 2e7 points); larger arguments (mu*r > 1e5) take the library path.
+__constant__ double c_sincos[16] = {
+    -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04, 2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,
+    4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05, -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,
+    6.36619772367581382433e-01 /* 2/pi */, -1.5707963267948966 /* -pi/2 hi */, -6.123233995736766e-17 /* -pi/2 lo */, 6755399441055744.0 /* 1.5 * 2^52 */};
+__device__ __noinline__ void sincos_large(double x, double* s, double* c) { sincos(x, s, c); }  // out of line: keeps the loops small
+__device__ __forceinline__ void sincos_real(double x, double* s, double* c) {
+  if (!(fabs(x) <= 1.0e5)) {  // also NaN / Inf
+    sincos_large(x, s, c);
+    return;
+  }
+  const double* k = c_sincos;
+  const double t = fma(x, k[12], k[15]);
+  const int q = __double2loint(t);  // nearest integer to x * 2/pi, low bits
+  const double n = t - k[15];
+  double r = fma(n, k[13], x);
+  r = fma(n, k[14], r);
+  const double z = r * r;
+  double ps = fma(z, k[5], k[4]);
+  double pc = fma(z, k[11], k[10]);
+  ps = fma(z, ps, k[3]);
+  pc = fma(z, pc, k[9]);
+  ps = fma(z, ps, k[2]);
+  pc = fma(z, pc, k[8]);
+  ps = fma(z, ps, k[1]);
+  pc = fma(z, pc, k[7]);
+  ps = fma(z, ps, k[0]);
+  pc = fma(z, pc, k[6]);
+  const double sr = fma(r * z, ps, r);
+  const double cr = fma(z, fma(z, pc, -0.5), 1.0);
+  const bool swap = q & 1;
+  const double s0 = swap ? cr : sr, c0 = swap ? sr : cr;
+  *s = __hiloint2double(__double2hiint(s0) ^ ((q & 2) << 30), __double2loint(s0));
+  *c = __hiloint2double(__double2hiint(c0) ^ (((q + 1) & 2) << 30), __double2loint(c0));
+}
+// FP32 twin: three-term Cody-Waite reduction with FMA, cephes minimax polynomials; max abs error 7.1e-8 for
+// |x| <= 4.5e4 (checked against double on 2e7 points); larger arguments take the library path.
+__device__ __noinline__ void sincos_large(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_real(float x, float* s, float* c) {
+  if (!(fabsf(x) <= 4.5e4f)) {
+    sincos_large(x, s, c);
+    return;
+  }
+  const float t = fmaf(x, 0.636619772367581f, 12582912.0f);  // 1.5 * 2^23: round to nearest integer
+  const int q = __float_as_int(t);
+  const float n = t - 12582912.0f;
+  float r = fmaf(n, -1.57079637050628662109375f, x);
+  r = fmaf(n, 4.37113882867379237e-8f, r);
+  r = fmaf(n, 1.71512451e-15f, r);
+  const float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  ps = fmaf(z, ps, -1.6666654611e-1f);
+  pc = fmaf(z, pc, 4.166664568298827e-2f);
+  const float sr = fmaf(r * z, ps, r);
+  const float cr = fmaf(z, fmaf(z, pc, -0.5f), 1.0f);
+  const bool swap = q & 1;
+  const float s0 = swap ? cr : sr, c0 = swap ? sr : cr;
+  *s = __int_as_float(__float_as_int(s0) ^ ((q & 2) << 30));
+  *c = __int_as_float(__float_as_int(c0) ^ (((q + 1) & 2) << 30));
+}
 
 // (G0, G1) of the gradient-type kernels: (-mu sin - cos/r, mu cos - sin/r) / r^2;  DIFF subtracts the Laplace part
 // through the half-angle identity cos(x) - 1 = -2 sin^2(x/2) (:640-647)

@@ -390,3 +390,30 @@ def test_particle_direct_session(sb, cpu_oracle, dtype):
     pd.SetKernelS2T("H", "W", sb.KERNELS["Helmholtz3D_FxU"])
     assert rel_err(pd.EvalDirect(None, "W", 2), cpu_oracle.eval("Helmholtz3D_FxU", rh, None, fh, r_trg[:900], dtype=dtype)) <= tol
     pd.close()
+
+
+@pytest.mark.parametrize("kernel", ["Helmholtz3D_FxU", "Helmholtz3D_FxdU", "HelmholtzDiff3D_FxdU"])
+def test_helmholtz_wavenumbers_cover_both_sincos_paths(sb, cpu_oracle, kernel):
+    """The device sin/cos (csrc/pair_math.cuh sincos_real) has a polynomial path for |mu r| <= 1e5 (FP32: 4.5e4) and
+    the library path beyond.  The phase mu*r carries the rounding error of r (1e-16 r) times mu, in the reference as much
+    as here, so the gate scales with the wavenumber."""
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    Ns, Nt = 3000, 2000
+    r_src, n_src, v_src, r_trg = synth.cube(Ns, Nt, k0, nd)
+    K = sb.GenericKernel(kernel)
+    for mu, tol64, tol32 in ((40.0, 1e-12, 5e-5), (3.0e3, 1e-11, None), (3.0e5, 1e-9, None)):
+        K.SetCtxPtr(mu)
+        got = K.Eval(None, r_trg, r_src, n_src, v_src)
+        want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg, ctx=mu)
+        assert np.all(np.isfinite(got)) and rel_err(got, want) <= tol64, (kernel, mu, rel_err(got, want))
+        if tol32:
+            f = lambda a: None if a is None else a.astype(np.float32)
+            got32 = K.Eval(None, f(r_trg), f(r_src), f(n_src), f(v_src), dtype=np.float32)
+            want32 = cpu_oracle.eval(kernel, f(r_src), f(n_src), f(v_src), f(r_trg), dtype=np.float64, ctx=mu)
+            assert rel_err(got32, want32) <= tol32, (kernel, mu, rel_err(got32, want32))
+    # FP32 beyond its polynomial range: library path, finite and close to the FP64 evaluation at FP32 phase accuracy
+    K.SetCtxPtr(6.0e4)
+    f = lambda a: None if a is None else a.astype(np.float32)
+    got32 = K.Eval(None, f(r_trg), f(r_src), f(n_src), f(v_src), dtype=np.float32)
+    assert np.all(np.isfinite(got32))

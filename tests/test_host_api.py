@@ -133,6 +133,7 @@ def test_sass_evidence_of_the_b200_design(sbm):
     funcs = {m.group(1): m.group(2) for m in re.finditer(r"Function : (\S+)\n(.*?)(?=Function :|\Z)", txt, flags=re.S)}
     smem = [b for n, b in funcs.items() if "eval_pairs_kernel" in n]
     const = [b for n, b in funcs.items() if "eval_pairs_const_kernel" in n]
+    helmholtz = {id(b) for n, b in funcs.items() if re.search(r"eval_pairs_const_kernelI[df]Li1[2-5]E", n)}  # kernel ids 12-15
     assert len(smem) >= 50 and len(const) >= 25
     for body in smem:
         assert "UBLKCP" in body and "SYNCS" in body
@@ -143,6 +144,7 @@ def test_sass_evidence_of_the_b200_design(sbm):
         assert re.search(r"LDCU(\.\d+)? UR\d+, c\[0x3\]", body)
         # the only vector loads from the bank are the two one-off reads of the masked/unmasked decision (the probe's flags
         # and this CTA's coincidence-bit word), never the source records inside the loops
-        assert len(re.findall(r" LDC(\.\d+)? R\d+, c\[0x3\]", body)) <= 2
+        # (the Helmholtz kernels also load sincos polynomial coefficients from the bank: exempt)
+        assert id(body) in helmholtz or len(re.findall(r" LDC(\.\d+)? R\d+, c\[0x3\]", body)) <= 2
         assert len(re.findall(r"[DF](FMA|MUL|ADD) [^;]*UR\d+", body)) >= 40
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", sbm.LIB_PATH], capture_output=True, text=True).stdout

@@ -42,6 +42,7 @@ def time_eval(kernel, dtype, Ns, Nt, reps=3, digits=-1):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--kernels", default="", help="comma-separated substring filter on kernel names")
     ap.add_argument("--paths", action="store_true", help="compare the Eval paths at shard sizes (Stokes3D_FxU f64)")
     args = ap.parse_args()
     sb.load_library()
@@ -62,6 +63,8 @@ def main():
     print("\n| kernel | Real | Ns x Nt | path (grid, launches) | ms | Gpair/s | TFLOP/s (F_alg) | frac of measured peak |\n|---|---|---|---|---|---|---|---|")
     sizes = [(1 << 16, 1 << 16), (1 << 20, 1 << 17)] if args.quick else [(20000, 20000), (1 << 20, 1 << 17), (1 << 19, 1 << 19)]
     for kernel in DIMS:
+        if args.kernels and not any(f in kernel for f in args.kernels.split(",")):
+            continue
         for dtype in (np.float64, np.float32):
             for Ns, Nt in sizes:
                 ms, plan = time_eval(kernel, dtype, Ns, Nt)
