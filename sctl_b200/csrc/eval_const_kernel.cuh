@@ -9,8 +9,8 @@
 // accumulate FMAs are (ceiling 93.6 %).
 //
 // The constant bank cannot be written from the device, so the host streams the packed sources through it in chunks
-// of CONST_PACK_BYTES (cudaMemcpyToSymbolAsync, device to device) and launches this kernel once per chunk; every
-// launch adds scale * (chunk's partial sum) to v_trg.  Targets stay register-resident for the whole chunk, T per
+// (cudaMemcpyToSymbolAsync, device to device; ConstGeom below) and launches this kernel once per chunk; every
+// launch adds scale * (chunk's partial sum) to its accumulation buffer.  Targets stay register-resident for the whole chunk, T per
 // thread.  When there are too few target blocks to balance 148 SMs, the chunk is split CL ways along grid.y and the
 // CL CTAs that own the same targets form a thread-block cluster: partial sums are combined through distributed
 // shared memory in rank order (deterministic, no atomics, no scratch traffic).
@@ -26,8 +26,9 @@ namespace sctl_cuda {
 constexpr int CONST_PACK_BYTES = 64 * 1024 - 1024;  // leave room for the compiler's own bank-3 constants
 __constant__ double c_src_pack[CONST_PACK_BYTES / 8];
 // [0]: the coincidence probe's verdict for the call in flight (0 = no source/target pair can have r2 < 2^-1022, so the
-// unmasked loop is exact); [1]: 1 = the per-CTA bits that refine a verdict of 1 are not usable.  Copied device-to-device from the probe's flag, so the choice needs no host round trip, and
-// read with LDCU, so the branch on it is uniform and the loops keep their uniform-register operands.
+// unmasked loop is exact); [1]: 1 = the per-CTA bits that refine a verdict of 1 are not usable.  Copied device-to-device
+// from the probe's flags, so the choice needs no host round trip, and read from the constant bank, so the branch on it
+// is uniform and the loops keep their uniform-register operands.
 __constant__ int c_eval_must_mask[4];
 
 template <class Real> struct ConstEvalArgs {

@@ -278,9 +278,9 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
   return 0;
 }
 
-// Chunk-streaming path: for every CONST_PACK_BYTES of packed sources, copy them into the constant bank (device to
-// device, stream ordered) and launch eval_pairs_const_kernel over all targets.  Each launch costs a fixed ~20 us
-// (kernel boundary + cold constant cache), so the path is used only when a chunk x Nt is >= ~2 ms of work.
+// Chunk-streaming path: the packed sources go through the constant bank one chunk segment at a time (device to device,
+// stream ordered), one eval_pairs_const_kernel launch over all targets per chunk.  Consecutive chunks use different
+// slices of the bank on different streams, so a launch's ramp and tail overlap its neighbours' (eval_const_kernel.cuh).
 
 template <class Real> int const_banks_wanted() {
   return (int)std::max<int64_t>(1, std::min<int64_t>(sizeof(Real) == 8 ? g.opt.const_banks : g.opt.const_banks_fp32, CONST_MAX_BANKS));
