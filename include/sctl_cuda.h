@@ -197,6 +197,12 @@ int sctl_cuda_set_option(const char* name, int64_t value);
 /* Back to the built-in defaults. */
 int sctl_cuda_reset_options(void);
 
+/* Layout of the constant-bank path for one call, exposed for host-side tests (no GPU needed): slices in flight, records
+ * per launch, 32-bit words of coincidence bits per chunk (0: none), bytes between slices, bytes per record, bytes per
+ * chunk segment in HBM, number of launches. */
+int sctl_cuda_const_geometry(int kernel_id, int real_bytes, int64_t Ns, int64_t Nt, int banks_wanted, int* banks, int* chunk, int* row_words,
+                             int* bank_stride, int* rec_bytes, int64_t* seg_bytes, int64_t* n_chunks);
+
 /* The grid planner, exposed for host-side tests (no GPU needed): for Nt targets in blocks of `tpb`, Ns sources
  * and `slots` resident CTAs (SMs x CTAs/SM) returns the number of source chunks, their length and the fraction
  * of the last wave that does useful work. */

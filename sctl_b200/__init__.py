@@ -54,6 +54,7 @@ def load_library():
     L.sctl_cuda_last_plan.argtypes = [ip, ip, ip, ip, ip, ip, dp]
     L.sctl_cuda_fma_peak.argtypes = [i, C.c_double, dp]
     L.sctl_cuda_set_option.argtypes = [C.c_char_p, i64]
+    L.sctl_cuda_const_geometry.argtypes = [i, i, i64, i64, i, ip, ip, ip, ip, ip, C.POINTER(i64), C.POINTER(i64)]
     L.sctl_cuda_direct_create.argtypes = [i, i, C.POINTER(vp)]
     L.sctl_cuda_direct_destroy.argtypes = [vp]
     L.sctl_cuda_direct_set_src_coord.argtypes = [vp, i, i64, vp, vp, i]
@@ -128,6 +129,14 @@ def last_plan():
 def set_option(name, value):
     """sctl_cuda_set_option: Eval path selection and tuning knobs (include/sctl_cuda.h lists them)."""
     _check(load_library().sctl_cuda_set_option(name.encode(), int(value)))
+
+
+def const_geometry(kernel, real_bytes, Ns, Nt, banks_wanted=2):
+    """Layout of the constant-bank path for one call (csrc/eval_const_kernel.cuh ConstGeom): pure host logic."""
+    v = [C.c_int() for _ in range(5)]
+    w = [C.c_int64() for _ in range(2)]
+    _check(load_library().sctl_cuda_const_geometry(_kid(kernel), real_bytes, Ns, Nt, banks_wanted, *[C.byref(x) for x in v], *[C.byref(x) for x in w]))
+    return dict(banks=v[0].value, chunk=v[1].value, row_words=v[2].value, bank_stride=v[3].value, rec_bytes=v[4].value, seg_bytes=w[0].value, n_chunks=w[1].value)
 
 
 def reset_options():

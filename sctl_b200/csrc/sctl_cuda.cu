@@ -1099,6 +1099,45 @@ int sctl_cuda_plan_eval(int64_t Ns, int64_t Nt, int tpb, int slots, int min_chun
   return 0;
 }
 
+int sctl_cuda_const_geometry(int kernel_id, int real_bytes, int64_t Ns, int64_t Nt, int banks_wanted, int* banks, int* chunk, int* row_words, int* bank_stride,
+                             int* rec_bytes, int64_t* seg_bytes, int64_t* n_chunks) {
+  if (check_common(kernel_id, real_bytes, Ns, Nt)) return 1;
+  if (banks_wanted < 1 || banks_wanted > CONST_MAX_BANKS) return fail("banks_wanted must be in [1, %d]", CONST_MAX_BANKS);
+  ConstGeom cg = {};
+#define SCTL_CUDA_CASE(K)                                                                                         \
+  case K:                                                                                                         \
+    cg = real_bytes == 8 ? const_geometry<double, K>(Ns, const_target_blocks<double>(Nt), banks_wanted, true)     \
+                         : const_geometry<float, K>(Ns, const_target_blocks<float>(Nt), banks_wanted, true);      \
+    break;
+  switch (kernel_id) {
+    SCTL_CUDA_CASE(LAPLACE3D_FXU)
+    SCTL_CUDA_CASE(LAPLACE3D_DXU)
+    SCTL_CUDA_CASE(LAPLACE3D_FXDU)
+    SCTL_CUDA_CASE(STOKES3D_FXU)
+    SCTL_CUDA_CASE(STOKES3D_DXU)
+    SCTL_CUDA_CASE(STOKES3D_FXT)
+    SCTL_CUDA_CASE(STOKES3D_FSXU)
+    SCTL_CUDA_CASE(STOKES3D_FXUP)
+    SCTL_CUDA_CASE(LAPLACE3D_FXD2U)
+    SCTL_CUDA_CASE(LAPLACE3D_DXDU)
+    SCTL_CUDA_CASE(BIOTSAVART3D_FXU)
+    SCTL_CUDA_CASE(BIOTSAVART3D_FXDU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_FXU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_DXU)
+    SCTL_CUDA_CASE(HELMHOLTZ3D_FXDU)
+    SCTL_CUDA_CASE(HELMHOLTZDIFF3D_FXDU)
+  }
+#undef SCTL_CUDA_CASE
+  if (banks) *banks = cg.banks;
+  if (chunk) *chunk = cg.chunk;
+  if (row_words) *row_words = cg.row_words;
+  if (bank_stride) *bank_stride = cg.bank_stride;
+  if (rec_bytes) *rec_bytes = cg.rec_bytes;
+  if (seg_bytes) *seg_bytes = cg.seg_bytes;
+  if (n_chunks) *n_chunks = cg.n_chunks;
+  return 0;
+}
+
 int sctl_cuda_fma_peak(int real_bytes, double ms, double* tflops) {
   if (!tflops) return fail("null output pointer");
   if (visible_devices() < 1) return fail("no CUDA device available");

@@ -73,6 +73,28 @@ def test_planner_fills_waves(sbm):
         assert p["n_split"] * p["chunk"] >= Ns and (p["n_split"] - 1) * p["chunk"] < Ns  # chunks tile the sources, none empty
 
 
+def test_constant_bank_geometry(sbm):
+    """ConstGeom (csrc/eval_const_kernel.cuh): slices never overlap, a segment fits its slice, chunks tile the sources,
+    the bit row covers every target block, too few chunks fall back to one slice, too many target blocks drop the bits."""
+    for kernel in ("Laplace3D_FxU", "Stokes3D_FxU", "Stokes3D_DxU", "BiotSavart3D_FxdU"):
+        for rb in (8, 4):
+            tpb = 512 if rb == 8 else 512  # CONST_NT * CONST_T: 256 x 2 (FP64), 128 x 4 (FP32)
+            for Ns, Nt, banks in ((1 << 20, 1 << 20, 2), (1 << 20, 1 << 17, 4), (5, 40000, 2), (9000, (1 << 18) + 77, 2), (1 << 22, 1 << 22, 2), (3000, 1 << 25, 2)):
+                g = sbm.const_geometry(kernel, rb, Ns, Nt, banks)
+                assert g["banks"] in (1, banks) and g["banks"] * g["bank_stride"] <= 63 * 1024 and g["bank_stride"] % 16 == 0
+                assert g["chunk"] >= 1 and g["chunk"] * g["rec_bytes"] + g["row_words"] * 4 <= g["bank_stride"]
+                assert g["seg_bytes"] == g["chunk"] * g["rec_bytes"] + g["row_words"] * 4 and g["seg_bytes"] % 16 == 0
+                assert g["n_chunks"] * g["chunk"] >= Ns > (g["n_chunks"] - 1) * g["chunk"]
+                assert g["banks"] == 1 or g["n_chunks"] >= 2 * g["banks"]
+                n_tb = -(-Nt // tpb)
+                assert g["row_words"] == 0 or g["row_words"] * 32 >= n_tb
+                assert (g["row_words"] > 0) == (-(-n_tb // 32) * 4 <= g["bank_stride"] // 8)
+    g = sbm.const_geometry("Stokes3D_FxU", 8, 1 << 20, 1 << 20, 2)
+    assert (g["banks"], g["rec_bytes"], g["row_words"], g["chunk"]) == (2, 48, 64, 666)
+    assert sbm.const_geometry("Stokes3D_FxU", 8, 5, 40000, 2)["banks"] == 1
+    assert sbm.const_geometry("Stokes3D_FxU", 8, 3000, 1 << 25, 2)["row_words"] == 0
+
+
 def test_compute_fails_loudly_without_gpu(sbm):
     if sbm.device_count() > 0:
         pytest.skip("a GPU is present")
