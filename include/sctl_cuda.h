@@ -154,9 +154,11 @@ int sctl_cuda_direct_eval(sctl_cuda_direct_t h, int trg, int digits, void* U, in
  * reference's variables: f_dsp = elem_nds_dsp[elem], far_dsp = elem_nds_dsp_far[elem], ns = elem_nds_cnt[elem],
  * u_dsp = near_elem_dsp[elem] + t0, nt = near_blk_cnt[blk], k_dsp = K_near_dsp[elem]*K0*K1 + t0*K1*ns*K0.
  *   set_matrix       upload K_near as the CPU singular/near quadrature left it; it then stays in HBM
- *   subtract_direct  "KNearSubtract" (:1165-1240) for the case without a density operator and without
- *                    trg_normal_dot_prod: K_b[(t*K1+k1)][(s*K0+k0)] -= wts[s] * KernelMatrix[(s*K0+k0)][(t*K1+k1)],
- *                    every block in one launch
+ *   subtract_direct  "KNearSubtract" (:1165-1240) for element lists without a density operator:
+ *                    K_b[(t*K1+k1)][(s*K0+k0)] -= wts[s] * KernelMatrix[(s*K0+k0)][(t*K1+k1)], every block in one launch.
+ *                    With Xn_trg (trg_normal_dot_prod, :1186-1200) the kernel's 3*K1 target components are contracted
+ *                    with the target normals first, sum_l KernelMatrix[..][(t*K1+k1)*3+l] * Xn_trg[t*3+l]; the session
+ *                    is then created with K1 = (kernel target dim) / 3
  *   apply            "EvalNear" (:1324-1340): U_b = K_b * F_b for every block in one launch (overwrites U; blocks
  *                    without sources give zeros, :1327-1331); F and U are host arrays, only they cross PCIe
  *   get_matrix       download K (tests)
@@ -169,7 +171,7 @@ int sctl_cuda_near_sizes(sctl_cuda_near_t h, int64_t* K_len, int64_t* nF, int64_
 int sctl_cuda_near_set_matrix(sctl_cuda_near_t h, const void* K, int64_t n_reals);
 int sctl_cuda_near_get_matrix(sctl_cuda_near_t h, void* K, int64_t n_reals);
 int sctl_cuda_near_subtract_direct(sctl_cuda_near_t h, int kernel_id, int digits, int64_t Ns, const void* Xs, const void* Xn, const void* wts,
-                                   int64_t Nt, const void* Xt, const void* ctx, int64_t ctx_bytes);
+                                   int64_t Nt, const void* Xt, const void* Xn_trg /* NULL, or trg_normal_dot_prod */, const void* ctx, int64_t ctx_bytes);
 int sctl_cuda_near_apply(sctl_cuda_near_t h, const void* F, int64_t nF, void* U, int64_t nU);
 
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:

@@ -54,9 +54,9 @@ template <class Real> class NearBlocks {
     if (sctl_cuda_near_get_matrix(h_, K_near.Dim() ? &K_near[0] : nullptr, K_near.Dim())) detail::die("sctl_cuda_near_get_matrix");
   }
 
-  // K_near_[i][j] -= wts[s] * KernelMatrix[j][i] for every block (element lists without a density operator, no
-  // trg_normal_dot_prod); ker supplies the kernel id (by Name()) and its context pointer.
-  template <class Kernel, class Vec> void SubtractDirect(const Kernel& ker, Integer digits, const Vec& X_far, const Vec& Xn_far, const Vec& wts_far, const Vec& Xtrg_near) {
+  // K_near_[i][j] -= wts[s] * KernelMatrix[j][i] for every block (element lists without a density operator); ker supplies the kernel id (by Name()) and its context pointer.
+  // Xn_trg_near non-empty selects trg_normal_dot_prod (:1186-1200); the object is then built with KDIM1 = Kernel::TrgDim()/3.
+  template <class Kernel, class Vec> void SubtractDirect(const Kernel& ker, Integer digits, const Vec& X_far, const Vec& Xn_far, const Vec& wts_far, const Vec& Xtrg_near, const Vec& Xn_trg_near = Vec()) {
     int id = -1;
     for (int k = 0;; k++) {
       const char* n = nullptr;
@@ -66,7 +66,8 @@ template <class Real> class NearBlocks {
     SCTL_CUDA_ASSERT(id >= 0);
     const void* ctx = ker.GetCtxPtr();
     if (sctl_cuda_near_subtract_direct(h_, id, (int)(digits >= 16 ? -1 : digits), X_far.Dim() / 3, X_far.Dim() ? &X_far[0] : nullptr, Xn_far.Dim() ? &Xn_far[0] : nullptr,
-                                       wts_far.Dim() ? &wts_far[0] : nullptr, Xtrg_near.Dim() / 3, Xtrg_near.Dim() ? &Xtrg_near[0] : nullptr, ctx, ctx ? (int64_t)sizeof(Real) : 0))
+                                       wts_far.Dim() ? &wts_far[0] : nullptr, Xtrg_near.Dim() / 3, Xtrg_near.Dim() ? &Xtrg_near[0] : nullptr, Xn_trg_near.Dim() ? &Xn_trg_near[0] : nullptr, ctx,
+                                       ctx ? (int64_t)sizeof(Real) : 0))
       detail::die("sctl_cuda_near_subtract_direct");
   }
 

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- numpy restatement of BoundaryIntegralOp's near-field block phases.
 
 Follows the reference loops in include/sctl/boundary_integral.txx:
-  * near_subtract  "KNearSubtract" (:1165-1240), the branch without trg_normal_dot_prod and with an empty K_direct
+  * near_subtract  "KNearSubtract" (:1165-1240), both trg_normal_dot_prod branches, with an empty K_direct
     (element lists whose FarFieldDensityOperatorTranspose is the identity): Mker = KernelMatrix(Xtrg_near_, X, Xn)
     (:1196-1197), rows scaled by wts[s] (:1198-1205), K_near_[i][j] -= Mker[j][i] (:1219-1229);
   * near_apply     "EvalNear" (:1324-1340): U_ = K_near_ * F_ per block; blocks without sources give zeros (:1327-1331).
@@ -10,7 +10,8 @@ Block table columns as in include/sctl_cuda.h (f_dsp, far_dsp, ns, u_dsp, nt, k_
 import numpy as np
 
 
-def near_subtract(orc, kernel, k0, k1, nd, tab, K, Xs, Xn, wts, Xt, dtype=np.float64):
+def near_subtract(orc, kernel, k0, k1, nd, tab, K, Xs, Xn, wts, Xt, dtype=np.float64, Xn_trg=None):
+    """k1 is the kernel's target dimension; with Xn_trg (trg_normal_dot_prod, :1186-1200) the operator has k1/3 rows per target."""
     f_dsp, far_dsp, ns, u_dsp, nt, k_dsp = tab
     K = np.array(K, dtype=dtype).reshape(-1)
     Xs, Xt = np.asarray(Xs, dtype=dtype).reshape(-1, 3), np.asarray(Xt, dtype=dtype).reshape(-1, 3)
@@ -23,7 +24,12 @@ def near_subtract(orc, kernel, k0, k1, nd, tab, K, Xs, Xn, wts, Xt, dtype=np.flo
         t = slice(u_dsp[b], u_dsp[b] + nt[b])
         M = orc.kernel_matrix(kernel, Xs[s].reshape(-1), None if Xn is None else Xn[s].reshape(-1), Xt[t].reshape(-1), dtype=dtype)  # (ns*k0) x (nt*k1)
         M = M * np.repeat(wts[s], k0)[:, None]
-        rows, cols = nt[b] * k1, ns[b] * k0
+        k1r = k1
+        if Xn_trg is not None:  # Mker[s*K0+k0][t*K1_+k1] = sum_l Mker_[s*K0+k0][(t*K1_+k1)*3+l] * wts[s] * Xn_trg[t*3+l]   (:1190-1199)
+            k1r = k1 // 3
+            nrm = np.asarray(Xn_trg, dtype=dtype).reshape(-1, 3)[t]
+            M = np.einsum("atkl,tl->atk", M.reshape(ns[b] * k0, nt[b], k1r, 3), nrm).reshape(ns[b] * k0, nt[b] * k1r)
+        rows, cols = nt[b] * k1r, ns[b] * k0
         blk = K[k_dsp[b]:k_dsp[b] + rows * cols].reshape(rows, cols)
         blk -= M.T.astype(dtype)
     return K

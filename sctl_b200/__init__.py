@@ -68,7 +68,7 @@ def load_library():
     L.sctl_cuda_near_sizes.argtypes = [vp, p64, p64, p64, p64]
     L.sctl_cuda_near_set_matrix.argtypes = [vp, vp, i64]
     L.sctl_cuda_near_get_matrix.argtypes = [vp, vp, i64]
-    L.sctl_cuda_near_subtract_direct.argtypes = [vp, i, i, i64, vp, vp, vp, i64, vp, vp, i64]
+    L.sctl_cuda_near_subtract_direct.argtypes = [vp, i, i, i64, vp, vp, vp, i64, vp, vp, vp, i64]
     L.sctl_cuda_near_apply.argtypes = [vp, vp, i64, vp, i64]
     L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
     _lib = L
@@ -465,8 +465,12 @@ class NearBlocks:
     setup phase (boundary_integral.txx:1165-1240) and the per-iteration "EvalNear" apply (:1324-1340) over one block
     list, with the operator resident in HBM.  Table columns are per block, in the units of include/sctl_cuda.h."""
 
-    def __init__(self, kernel, f_dsp, far_dsp, ns, u_dsp, nt, k_dsp, dtype=np.float64):
+    def __init__(self, kernel, f_dsp, far_dsp, ns, u_dsp, nt, k_dsp, dtype=np.float64, trg_normal_dot_prod=False):
         self.kernel = kernel if isinstance(kernel, GenericKernel) else GenericKernel(kernel)
+        self.trg_normal_dot_prod = bool(trg_normal_dot_prod)
+        if self.trg_normal_dot_prod and self.kernel.TrgDim() % 3:
+            raise SctlCudaError("trg_normal_dot_prod needs a kernel whose target dimension is a multiple of 3")
+        self.k1 = self.kernel.TrgDim() // 3 if self.trg_normal_dot_prod else self.kernel.TrgDim()  # KDIM1_ (boundary_integral.txx:1312)
         self._dtype = np.dtype(dtype).type
         cols = [np.ascontiguousarray(c, dtype=np.int64).reshape(-1) for c in (f_dsp, far_dsp, ns, u_dsp, nt, k_dsp)]
         n = cols[0].size
@@ -475,7 +479,7 @@ class NearBlocks:
         self._h = C.c_void_p()
         L = load_library()
         p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
-        _check(L.sctl_cuda_near_create(np.dtype(dtype).itemsize, self.kernel.SrcDim(), self.kernel.TrgDim(), n, *[p64(c) for c in cols], C.byref(self._h)))
+        _check(L.sctl_cuda_near_create(np.dtype(dtype).itemsize, self.kernel.SrcDim(), self.k1, n, *[p64(c) for c in cols], C.byref(self._h)))
         v = [C.c_int64() for _ in range(4)]
         _check(L.sctl_cuda_near_sizes(self._h, *[C.byref(x) for x in v]))
         self.K_len, self.nF, self.nU, self.n_far = [x.value for x in v]
@@ -500,12 +504,14 @@ class NearBlocks:
         _check(load_library().sctl_cuda_near_get_matrix(self._h, _np_ptr(K), K.size))
         return K
 
-    def subtract_direct(self, Xs, Xn, wts, Xt, digits=-1):
+    def subtract_direct(self, Xs, Xn, wts, Xt, Xn_trg=None, digits=-1):
         c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=self._dtype).reshape(-1)
-        Xs, Xn, wts, Xt = c(Xs), c(Xn), c(wts), c(Xt)
+        Xs, Xn, wts, Xt, Xn_trg = c(Xs), c(Xn), c(wts), c(Xt), c(Xn_trg)
+        if self.trg_normal_dot_prod != (Xn_trg is not None):
+            raise SctlCudaError("Xn_trg must be given exactly when the session was created with trg_normal_dot_prod")
         ctx, nb = self.kernel._ctx_arg(self._dtype)
         _check(load_library().sctl_cuda_near_subtract_direct(self._h, self.kernel.kernel_id, int(digits), Xs.size // 3, _np_ptr(Xs), _np_ptr(Xn), _np_ptr(wts),
-                                                             Xt.size // 3, _np_ptr(Xt), _np_ptr(ctx), nb))
+                                                             Xt.size // 3, _np_ptr(Xt), _np_ptr(Xn_trg), _np_ptr(ctx), nb))
 
     def apply(self, F, U=None):
         F = np.ascontiguousarray(F, dtype=self._dtype).reshape(-1)

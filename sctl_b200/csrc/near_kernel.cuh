@@ -50,20 +50,27 @@ template <class Real> __host__ __device__ constexpr int near_apply_rows() { retu
 // stores, which keeps several independent DRAM requests in flight per thread (a plain `*p -= x` loop serialises one
 // round trip per target).  The pair arithmetic is the KernelMatrix twin PairMatrix<KID> (pair_math.cuh), scaled per
 // entry like generic-kernel.txx:268,306, then by the weight (:1203).
-template <class Real, int KID, int RSQ>
+// NDOT: the trg_normal_dot_prod variant (:1186-1200): the kernel's K1 = 3*K1r target components are contracted with the
+// target normal, entry (k0, k1r) = sum_l u[k0][k1r*3+l] * n_t[l], and the operator block has K1r rows per target.
+template <class Real, int KID, int RSQ, bool NDOT>
 __global__ void __launch_bounds__(NEAR_SUB_THREADS) near_subtract_kernel(const NearBlocks nb, const Real* __restrict__ Xs, const Real* __restrict__ Xn, const Real* __restrict__ wts,
-                                                                         const Real* __restrict__ Xt, Real* __restrict__ K, Real scale, Real ctx0) {
-  constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
+                                                                         const Real* __restrict__ Xt, const Real* __restrict__ Xn_trg, Real* __restrict__ K, Real scale, Real ctx0) {
+  constexpr int K0 = KerTraits<KID>::K0, KU = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
+  constexpr int K1 = NDOT ? (KU >= 3 ? KU / 3 : 1) : KU;  // rows per target in the operator block
   constexpr int KK = K0 * K1;
   constexpr int TU = KK == 1 ? 8 : (KK == 2 ? 4 : (KK <= 4 ? 2 : 1));  // targets whose entries are loaded together
   __shared__ Real xt_s[NEAR_SUB_TRG][3];
+  __shared__ Real nt_s[NEAR_SUB_TRG][3];
   for (int64_t w = blockIdx.x; w < nb.n_items; w += gridDim.x) {
     const int b = nb.item_blk[w];
     const int64_t t0 = nb.item_t0[w];
     const int64_t ns = nb.ns[b], nt = nb.nt[b];
     const int n_t = (int)min((int64_t)NEAR_SUB_TRG, nt - t0);
     __syncthreads();
-    if (threadIdx.x < n_t * 3) xt_s[threadIdx.x / 3][threadIdx.x % 3] = Xt[(nb.u_dsp[b] + t0) * 3 + threadIdx.x];  // NEAR_SUB_TRG * 3 <= NEAR_SUB_THREADS
+    if (threadIdx.x < n_t * 3) {  // NEAR_SUB_TRG * 3 <= NEAR_SUB_THREADS
+      xt_s[threadIdx.x / 3][threadIdx.x % 3] = Xt[(nb.u_dsp[b] + t0) * 3 + threadIdx.x];
+      if (NDOT) nt_s[threadIdx.x / 3][threadIdx.x % 3] = Xn_trg[(nb.u_dsp[b] + t0) * 3 + threadIdx.x];
+    }
     __syncthreads();
     int lanes = NEAR_SUB_THREADS;  // source lanes: the smallest power of two >= ns, at least 32 (whole warps share a row)
     while (lanes > 32 && (lanes >> 1) >= ns) lanes >>= 1;
@@ -97,9 +104,16 @@ __global__ void __launch_bounds__(NEAR_SUB_THREADS) near_subtract_kernel(const N
             Real dx[3] = {xt_s[t][0] - xs[0], xt_s[t][1] - xs[1], xt_s[t][2] - xs[2]};
             const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
             const Real rinv = rsqrt_masked<RSQ>(r2);
-            Real u[KK];
-            if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u, dx, rinv, n, r2, ctx0);
-            else PairMatrix<KID, Real>::run(u, dx, rinv, n);
+            Real uu[K0 * KU], u[KK];
+            if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(uu, dx, rinv, n, r2, ctx0);
+            else PairMatrix<KID, Real>::run(uu, dx, rinv, n);
+#pragma unroll
+            for (int k0 = 0; k0 < K0; k0++)
+#pragma unroll
+              for (int k1 = 0; k1 < K1; k1++) {
+                if constexpr (NDOT) u[k0 * K1 + k1] = fma(uu[k0 * KU + k1 * 3 + 2], nt_s[t][2], fma(uu[k0 * KU + k1 * 3 + 1], nt_s[t][1], uu[k0 * KU + k1 * 3 + 0] * nt_s[t][0]));
+                else u[k0 * K1 + k1] = uu[k0 * KU + k1];
+              }
 #pragma unroll
             for (int k1 = 0; k1 < K1; k1++)
 #pragma unroll

@@ -89,3 +89,34 @@ def test_near_blocks_errors_and_empty(sb):
     with pytest.raises(sb.SctlCudaError):
         sb.NearBlocks(sb.Stokes3D_FxU, i64(-1), one, one, one, one, one)
     nb.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", ["Laplace3D_FxdU", "Stokes3D_FxT", "Laplace3D_DxdU"])
+def test_near_blocks_trg_normal_dot_prod(sb, cpu_oracle, kernel, dtype):
+    """trg_normal_dot_prod (boundary_integral.txx:1186-1200): the kernel's 3*K1_ target components are contracted with the
+    target normals before the weighted transpose-subtract; the operator block then has K1_ rows per target."""
+    from oracle import near_blocks as nbo
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    k1r = k1 // 3
+    tab, n_nodes, n_far, n_trg, K_len = block_list(25, k0, k1r, seed=11)
+    Xs, Xn, _, Xt = synth.cube(n_far, n_trg, k0, 3, dtype=dtype)
+    Xn = Xn if nd else None
+    Xn_trg = (synth.splitmix_u01(31, n_trg * 3) - 0.5).astype(dtype)
+    wts = (synth.splitmix_u01(21, n_far) * 0.01 + 0.001).astype(dtype)
+    K0_ = (synth.splitmix_u01(22, K_len) - 0.5).astype(dtype)
+    nb = sb.NearBlocks(sb.KERNELS[kernel], *tab, dtype=dtype, trg_normal_dot_prod=True)
+    assert (nb.K_len, nb.nU) == (K_len, n_trg * k1r)
+    nb.set_matrix(K0_)
+    with pytest.raises(sb.SctlCudaError, match="Xn_trg"):
+        nb.subtract_direct(Xs, Xn, wts, Xt)
+    nb.subtract_direct(Xs, Xn, wts, Xt, Xn_trg)
+    want_K = nbo.near_subtract(cpu_oracle, kernel, k0, k1, nd, tab, K0_, Xs, Xn, wts, Xt, dtype=dtype, Xn_trg=Xn_trg)
+    assert rel_err(nb.get_matrix(), want_K) <= TOL[dtype]
+    F = (synth.splitmix_u01(23, n_nodes * k0) - 0.5).astype(dtype)
+    U = nb.apply(F)
+    assert rel_err(U, nbo.near_apply(k0, k1r, tab, want_K.astype(np.float64), F.astype(np.float64), n_trg * k1r)) <= TOL[dtype]
+    nb.close()
+    with pytest.raises(sb.SctlCudaError, match="multiple of 3"):
+        sb.NearBlocks(sb.Laplace3D_FxU, *tab, dtype=dtype, trg_normal_dot_prod=True)
