@@ -129,7 +129,8 @@ int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes,
  * once and stay in HBM, an apply ships only the density in and the potential out.  Sources and targets are
  * addressed by small non-negative slot numbers chosen by the caller (the C++ mirror maps ParticleFMM's names to
  * them).  With n_gpus > 1 the targets are sharded by contiguous block over GPUs 0..n_gpus-1 (the rule of
- * fmm-wrapper.txx:568) and every GPU holds all sources; no reduction, so results do not depend on n_gpus.
+ * fmm-wrapper.txx:568) and every GPU holds all sources; no reduction between GPUs (results agree to rounding
+ * for any n_gpus: a shard may split the sources differently from the whole target set).
  *   set_src_coord    ParticleFMM::SetSrcCoord(name, X, Xn)   (fmm-wrapper.hpp:166)  normal_dim 0 or 3
  *   set_src_density  ParticleFMM::SetSrcDensity(name, F)     (:174)  n_reals = Ns * K0 of the kernels that use it
  *   set_trg_coord    ParticleFMM::SetTrgCoord(name, X)       (:182)

@@ -39,7 +39,7 @@ template <class Real, Integer DIM = 3> class ParticleDirect {
   ParticleDirect(const ParticleDirect&) = delete;
   ParticleDirect& operator=(const ParticleDirect&) = delete;
 
-  // n_gpus > 1 shards every target set by contiguous block over GPUs 0..n_gpus-1 (results do not depend on it)
+  // n_gpus > 1 shards every target set by contiguous block over GPUs 0..n_gpus-1 (results agree to rounding for any n_gpus)
   explicit ParticleDirect(int n_gpus = 1) : h_(nullptr), digits_(10) {  // default accuracy: fmm-wrapper.txx:205
     if (sctl_cuda_direct_create(detail::real_bytes<Real>::value, n_gpus, &h_)) detail::die("sctl_cuda_direct_create");
   }

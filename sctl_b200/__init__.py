@@ -362,7 +362,7 @@ class ParticleDirect:
     """Device-resident direct evaluator: the ``ParticleFMM::EvalDirect`` analogue (fmm-wrapper.hpp:35-200,
     fmm-wrapper.txx:551-623) over ``sctl_cuda_direct_*``.  Same method names and argument meaning as ``ParticleFMM``
     for the subset EvalDirect uses; coordinates are uploaded once and stay in HBM, an apply ships only the density in
-    and the potential out.  ``n_gpus > 1`` shards the targets over GPUs 0..n_gpus-1 (results do not depend on it)."""
+    and the potential out.  ``n_gpus > 1`` shards the targets over GPUs 0..n_gpus-1 (results agree to rounding for any n_gpus)."""
 
     def __init__(self, dtype=np.float64, n_gpus=1):
         self._dtype = np.dtype(dtype).type

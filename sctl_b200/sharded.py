@@ -5,7 +5,8 @@ per rank (:565-569) and an np-step source ring (:598-619) that serialises commun
 NVSwitch box every GPU reaches every peer at full bandwidth, so the ring is replaced by one round of broadcasts:
 rank q broadcasts its source slice into the same offsets of every rank's full source arrays (an all-gather with
 ragged counts), then every rank evaluates its own target shard against all sources.  No reduction is needed, so the
-per-target summation order is the single-GPU order and results do not depend on the number of ranks.
+per-target sum involves no cross-GPU partial sums; results agree to rounding for any number of ranks (a shard may
+split the sources differently from the whole target set).
 
 ``torch.distributed`` is plumbing only; the arithmetic goes through ``sctl_cuda_eval_device``.  The compute step is
 injectable so the partition / exchange logic can be tested with the gloo backend on CPU (tests/test_sharded_gloo.py).

