@@ -289,7 +289,7 @@ def main():
     k_ms = float(np.mean(ker_ms))
     achieved = my_pairs * F_ALG[kernel] / (k_ms * 1e-3) * 1e-12
     # DRAM bytes of one pair-kernel launch from the ncu --set full capture of this same workload
-    # (profiles/r1_ncu_eval_const_2banks_stokes_fxu_f64.md): 50.38 MB read + 0.02 MB written per constant-bank launch at 2^20
+    # (profiles/r1_ncu_eval_const_final_stokes_fxu_f64.md): 50.38 MB read + 0.02 MB written per constant-bank launch at 2^20
     # targets (r_trg + the v_trg read-modify-write; the write-back stays in L2); null for any other workload
     traffic = 50.40e6 if (kernel, args.log2n, rb, world) == ("Stokes3D_FxU", 20, 8, 1) else None
     const_path = plan["n_launches"] > 10  # one launch per source chunk (the ring paths need at most 5)

@@ -44,8 +44,11 @@ enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
 // and the host only selects it after coincidence_probe_kernel has shown that no (source, target) pair can have a
 // smaller r2 (eval_kernel.cuh); the two instructions cost ~3 % of the Stokes pair (profiles/r1_whatif.txt).
 template <int MODE, bool MASK = true> __device__ __forceinline__ double rsqrt_masked(double x) {
-  // One signed compare on the high word: false for zero, subnormal and negative inputs (NaN/Inf propagate as NaN,
-  // exactly as in the reference), then a select on the seed's high word; its low word is zero anyway.  Every
+  // One signed compare on the high word: false for zero, subnormal and negative inputs, then a select on the seed's high
+  // word; its low word is zero anyway.  NaN / Inf inputs are NOT masked and propagate as NaN.  (The reference's r2 > 0
+  // compare is false for NaN, so there a NaN pair is dropped by kernels that only multiply by rinv, e.g. Laplace3D_FxU,
+  // and still gives NaN wherever the kernel also multiplies by the displacement; inputs with NaN are outside the parity
+  // contract and the unmasked loop could not reproduce that distinction anyway.)  Every
   // register-reading instruction competes with the DFMA stream for register-file bandwidth on B200
   // (tools/probe.cu, probe4), so the mask is kept to compare + select.
   double ys;

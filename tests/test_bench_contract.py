@@ -40,3 +40,11 @@ def test_our_arm_line_small():
     assert d["gpu_launches"] >= 2 * d["steps"]
     assert d["parity"]["max_abs_err_over_vinf"] <= 1e-12
     assert d["cpu_baseline"]["value"] > 0 and d["value"] > d["cpu_baseline"]["value"]
+
+
+@pytest.mark.gpu
+def test_our_arm_surface_points_small():
+    """--points torus: surface nodes, targets == sources (every target has one r2 == 0 pair that must contribute 0)."""
+    d = _run(["--log2n", "14", "--points", "torus", "--steps", "2", "--warmup", "3", "--cpu-targets", "2048", "--no-e2e"])
+    assert "torus surface nodes" in d["config"]["workload"] and "targets == sources" in d["config"]["workload"]
+    assert d["parity"]["max_abs_err_over_vinf"] <= 1e-12 and d["value"] > 0
