@@ -5,7 +5,10 @@ Follows the reference loops in include/sctl/boundary_integral.txx:
     (element lists whose FarFieldDensityOperatorTranspose is the identity): Mker = KernelMatrix(Xtrg_near_, X, Xn)
     (:1196-1197), rows scaled by wts[s] (:1198-1205), K_near_[i][j] -= Mker[j][i] (:1219-1229);
   * near_apply     "EvalNear" (:1324-1340): U_ = K_near_ * F_ per block; blocks without sources give zeros (:1327-1331).
-KernelMatrix itself comes from the oracle object passed in (the C port or the unmodified reference).
+KernelMatrix itself comes from the oracle object passed in (the C port or the unmodified reference), which is pinned.
+PINNING: the block loops themselves (weight scaling, normal contraction, transpose-subtract, per-block GEMV, layouts)
+are restated from the cited lines and are NOT pinned against a run of the reference: they act on private state of
+BoundaryIntegralOp (K_near, near_blk_*) that the reference does not expose -- "parity unpinned" for that part.
 Block table columns as in include/sctl_cuda.h (f_dsp, far_dsp, ns, u_dsp, nt, k_dsp)."""
 import numpy as np
 
