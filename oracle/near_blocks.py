@@ -6,9 +6,10 @@ Follows the reference loops in include/sctl/boundary_integral.txx:
     (:1196-1197), rows scaled by wts[s] (:1198-1205), K_near_[i][j] -= Mker[j][i] (:1219-1229);
   * near_apply     "EvalNear" (:1324-1340): U_ = K_near_ * F_ per block; blocks without sources give zeros (:1327-1331).
 KernelMatrix itself comes from the oracle object passed in (the C port or the unmodified reference), which is pinned.
-PINNING: the block loops themselves (weight scaling, normal contraction, transpose-subtract, per-block GEMV, layouts)
-are restated from the cited lines and are NOT pinned against a run of the reference: they act on private state of
-BoundaryIntegralOp (K_near, near_blk_*) that the reference does not expose -- "parity unpinned" for that part.
+PINNING: the block loops act on private state of BoundaryIntegralOp (K_near, near_blk_*), so this numpy restatement is
+not run against the reference directly; the same device code that it checks is pinned against the reference's own
+BoundaryIntegralOp by tests/cpp/test_near_blocks_ref.cpp (private members opened in that test TU, K_near and
+ComputeNearInterac compared on a torus with non-empty near lists, with and without trg_normal_dot_prod).
 Block table columns as in include/sctl_cuda.h (f_dsp, far_dsp, ns, u_dsp, nt, k_dsp)."""
 import numpy as np
 

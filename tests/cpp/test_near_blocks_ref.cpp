@@ -1,0 +1,151 @@
+// tests/cpp/test_near_blocks_ref.cpp -- pins sctl_cuda::NearBlocks (GPU) against the reference's own BoundaryIntegralOp.
+//
+// The reference (unmodified headers, CPU, NOT routed through the drop-in) sets up a BoundaryIntegralOp on a torus of
+// 8 x 8-node patches whose far-field distance is positive, so its near lists are non-empty.  The element list keeps the
+// base-class NearInterac / SelfInterac defaults (empty matrices, boundary_integral.txx:536-546), so K_near is zero
+// before "KNearSubtract" (:1150-1158) and equals minus the weighted direct interactions after it (:1165-1240).  This
+// program is compiled with the class's private members opened (test infrastructure only) and
+//   1. builds sctl_cuda::NearBlocks from the reference's own near_blk_* / elem_* tables, lets the GPU subtract the direct
+//      part from a zero matrix and compares with the reference's K_near;
+//   2. applies it on the GPU, runs the reference's own scatter / accumulate tail (:1371-1383) on the result and compares
+//      with the reference's ComputeNearInterac.
+// Both with and without trg_normal_dot_prod.  Built only where /root/reference is mounted; the binary travels.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <string>
+#include <vector>
+#include <omp.h>
+
+#define private public
+#define protected public
+#include <sctl.hpp>
+#undef private
+#undef protected
+
+#include "sctl_cuda/near_blocks.hpp"
+
+using namespace sctl;
+
+static int n_fail = 0;
+#define CHECK(cond, ...)                               \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      n_fail++;                                        \
+      std::printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+      std::printf(__VA_ARGS__);                        \
+      std::printf("\n");                               \
+    }                                                  \
+  } while (0)
+
+template <class Real> class TorusPatchList : public ElementListBase<Real> {
+ public:
+  TorusPatchList(Long Nu, Long Nv, Real dist) : Nu_(Nu), Nv_(Nv), dist_(dist) {
+    const Real R = 1, a = (Real)0.25, two_pi = 2 * const_pi<Real>();
+    const Long N = Nu * Nv;
+    X_.ReInit(N * 3);
+    Xn_.ReInit(N * 3);
+    w_.ReInit(N);
+    Long idx = 0;
+    for (Long pu = 0; pu < Nu / 8; pu++)
+      for (Long pv = 0; pv < Nv / 8; pv++)
+        for (Long iu = 0; iu < 8; iu++)
+          for (Long iv = 0; iv < 8; iv++, idx++) {
+            const Real u = (pu * 8 + iu) * two_pi / Nu, v = (pv * 8 + iv) * two_pi / Nv;
+            const Real rho = R + a * std::cos(v);
+            X_[idx * 3 + 0] = rho * std::cos(u); X_[idx * 3 + 1] = rho * std::sin(u); X_[idx * 3 + 2] = a * std::sin(v);
+            Xn_[idx * 3 + 0] = std::cos(v) * std::cos(u); Xn_[idx * 3 + 1] = std::cos(v) * std::sin(u); Xn_[idx * 3 + 2] = std::sin(v);
+            w_[idx] = a * rho * (two_pi / Nu) * (two_pi / Nv);
+          }
+  }
+  Long Size() const override { return (Nu_ / 8) * (Nv_ / 8); }
+  void GetNodeCoord(Vector<Real>* X, Vector<Real>* Xn, Vector<Long>* cnt) const override {
+    if (X) *X = X_;
+    if (Xn) *Xn = Xn_;
+    if (cnt) { cnt->ReInit(Size()); for (Long i = 0; i < Size(); i++) (*cnt)[i] = 64; }
+  }
+  void GetFarFieldNodes(Vector<Real>& X, Vector<Real>& Xn, Vector<Real>& wts, Vector<Real>& dist_far, Vector<Long>& cnt, const Real tol) const override {
+    X = X_; Xn = Xn_; wts = w_;
+    dist_far.ReInit(w_.Dim());
+    for (auto& d : dist_far) d = dist_;  // positive: targets closer than this to an element go on its near list
+    cnt.ReInit(Size()); for (Long i = 0; i < Size(); i++) cnt[i] = 64;
+  }
+ private:
+  Long Nu_, Nv_;
+  Real dist_;
+  Vector<Real> X_, Xn_, w_;
+};
+
+template <class Real> static double rel_err(const Vector<Real>& a, const Vector<Real>& b) {
+  if (a.Dim() != b.Dim()) return 1e300;
+  double e = 0, m = 0;
+  for (Long i = 0; i < a.Dim(); i++) {
+    e = std::max(e, std::fabs((double)a[i] - (double)b[i]));
+    m = std::max(m, std::fabs((double)b[i]));
+  }
+  return m > 0 ? e / m : e;
+}
+
+template <class Real, class Kernel> static void run(const char* what, bool ndot, double tol) {
+  constexpr Integer KDIM0 = Kernel::SrcDim(), KDIM1 = Kernel::TrgDim();
+  const Integer KDIM1_ = ndot ? KDIM1 / 3 : KDIM1;
+  TorusPatchList<Real> elems(64, 32, (Real)0.2);
+  Kernel ker;
+  BoundaryIntegralOp<Real, Kernel> op(ker, ndot);
+  op.SetAccuracy((Real)1e-10);
+  op.AddElemList(elems);
+  const Long N = 64 * 32;
+  Vector<Real> F(N * KDIM0), U;
+  unsigned long long z = 0x9E3779B97F4A7C15ULL;
+  for (auto& f : F) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; f = (Real)((z >> 11) * (1.0 / 9007199254740992.0)) - (Real)0.5; }
+  op.ComputePotential(U, F);  // runs Setup: near lists, K_near (zero), KNearSubtract
+  const Long Nblk = op.near_blk_elem.Dim();
+  const Long Nelem = op.near_elem_cnt.Dim();
+  const Long Nnear = Nelem ? op.near_elem_dsp[Nelem - 1] + op.near_elem_cnt[Nelem - 1] : 0;
+  CHECK(Nblk > 0 && Nnear > N, "%s: near list unexpectedly small (blocks %ld, near pairs %ld)", what, (long)Nblk, (long)Nnear);
+
+  sctl_cuda::NearBlocks<Real> nb(KDIM0, KDIM1_, op.near_blk_elem, op.near_blk_t0, op.near_blk_cnt, op.elem_nds_cnt, op.elem_nds_dsp, op.elem_nds_dsp_far, op.near_elem_dsp,
+                                 op.K_near_dsp);
+  Vector<Real> Kzero(op.K_near.Dim()), Kgpu(op.K_near.Dim());
+  Kzero.SetZero();
+  nb.SetMatrix(Kzero);
+  if (ndot) nb.SubtractDirect(ker, -1 /* KernelMatrix<Real,false>: default digits, :1190,1197 */, op.X_far, op.Xn_far, op.wts_far, op.Xtrg_near, op.Xn_trg_near);
+  else nb.SubtractDirect(ker, -1 /* KernelMatrix<Real,false>: default digits, :1190,1197 */, op.X_far, op.Xn_far, op.wts_far, op.Xtrg_near);
+  nb.GetMatrix(Kgpu);
+  const double eK = rel_err(Kgpu, op.K_near);
+  CHECK(eK <= tol, "%s: K_near after KNearSubtract differs from the reference's by %.3e", what, eK);
+
+  // apply + the reference's own tail (boundary_integral.txx:1371-1383), against the reference's ComputeNearInterac
+  Vector<Real> U_near(Nnear * KDIM1_), Ugpu(N * KDIM1_), Uref;
+  nb.Apply(U_near, F);
+  op.comm_.ScatterForward(U_near, op.near_scatter_index);
+  Ugpu.SetZero();
+  for (Long i = 0; i < N; i++)
+    for (Long j = 0; j < op.near_trg_cnt[i]; j++)
+      for (Long k = 0; k < KDIM1_; k++) Ugpu[i * KDIM1_ + k] += U_near[(op.near_trg_dsp[i] + j) * KDIM1_ + k];
+  op.ComputeNearInterac(Uref, F);
+  const double eU = rel_err(Ugpu, Uref);
+  CHECK(eU <= tol, "%s: near-field potential differs from the reference's ComputeNearInterac by %.3e", what, eU);
+  std::printf("%-44s blocks %5ld  near pairs %7ld  K_near err %.2e  U err %.2e\n", what, (long)Nblk, (long)Nnear, eK, eU);
+}
+
+int main() {
+  run<double, Laplace3D_FxU>("Laplace3D_FxU f64", false, 1e-12);
+  run<double, Laplace3D_DxU>("Laplace3D_DxU f64", false, 1e-12);
+  run<double, Stokes3D_FxU>("Stokes3D_FxU f64", false, 1e-12);
+  run<double, Stokes3D_DxU>("Stokes3D_DxU f64", false, 1e-12);
+  run<double, Laplace3D_FxdU>("Laplace3D_FxdU f64 trg_normal_dot_prod", true, 1e-12);
+  run<double, Stokes3D_FxT>("Stokes3D_FxT f64 trg_normal_dot_prod", true, 1e-12);
+  run<float, Laplace3D_FxU>("Laplace3D_FxU f32", false, 2e-5);
+  run<float, Stokes3D_FxU>("Stokes3D_FxU f32", false, 2e-5);
+  std::printf("%s (%d check(s) failed)\n", n_fail ? "FAIL" : "PASS", n_fail);
+  return n_fail ? 1 : 0;
+}
