@@ -9,6 +9,7 @@
 //      part from a zero matrix and compares with the reference's K_near;
 //   2. applies it on the GPU, runs the reference's own scatter / accumulate tail (:1371-1383) on the result and compares
 //      with the reference's ComputeNearInterac.
+//   3. adds the far field from sctl_cuda::ParticleDirect and compares the sum with the reference's ComputePotential.
 // Both with and without trg_normal_dot_prod.  Built only where /root/reference is mounted; the binary travels.
 #include <algorithm>
 #include <chrono>
@@ -32,6 +33,7 @@
 #undef protected
 
 #include "sctl_cuda/near_blocks.hpp"
+#include "sctl_cuda/particle_direct.hpp"
 
 using namespace sctl;
 
@@ -134,7 +136,31 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
   op.ComputeNearInterac(Uref, F);
   const double eU = rel_err(Ugpu, Uref);
   CHECK(eU <= tol, "%s: near-field potential differs from the reference's ComputeNearInterac by %.3e", what, eU);
-  std::printf("%-44s blocks %5ld  near pairs %7ld  K_near err %.2e  U err %.2e\n", what, (long)Nblk, (long)Nnear, eK, eU);
+  // 3. the whole apply from the two sessions (INTEGRATION.md 3a + 3b): far field through the device-resident evaluator with
+  //    the reference's far-field nodes and F * wts (ComputeFarField, :1248-1309), plus the near correction above, against
+  //    the reference's ComputePotential (far + near, all on the CPU)
+  sctl_cuda::ParticleDirect<Real> pd;
+  pd.SetAccuracy(11);  // tol 1e-10 -> digits 11 (boundary_integral.txx:562)
+  pd.AddSrc("Src", ker, ker);
+  pd.AddTrg("Trg", ker, ker);
+  pd.SetKernelS2T("Src", "Trg", ker);
+  pd.SetSrcCoord("Src", op.X_far, op.Xn_far);
+  pd.SetTrgCoord("Trg", op.Xtrg);
+  Vector<Real> F_far(N * KDIM0), Ufar, Utot(N * KDIM1_);
+  for (Long i = 0; i < N; i++)
+    for (Long j = 0; j < KDIM0; j++) F_far[i * KDIM0 + j] = F[i * KDIM0 + j] * op.wts_far[i];
+  pd.SetSrcDensity("Src", F_far);
+  pd.Eval(Ufar, "Trg");
+  for (Long i = 0; i < N; i++)
+    for (Long k = 0; k < KDIM1_; k++) {
+      Real v = 0;
+      if (ndot) for (Long l = 0; l < 3; l++) v += Ufar[(i * KDIM1_ + k) * 3 + l] * op.Xn_trg[i * 3 + l];
+      else v = Ufar[i * KDIM1_ + k];
+      Utot[i * KDIM1_ + k] = v + Ugpu[i * KDIM1_ + k];
+    }
+  const double eT = rel_err(Utot, U);
+  CHECK(eT <= tol, "%s: far + near potential differs from the reference's ComputePotential by %.3e", what, eT);
+  std::printf("%-44s blocks %5ld  near pairs %7ld  K_near err %.2e  near U err %.2e  ComputePotential err %.2e\n", what, (long)Nblk, (long)Nnear, eK, eU, eT);
 }
 
 int main() {

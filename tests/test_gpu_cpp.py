@@ -51,7 +51,8 @@ def test_near_blocks_against_reference_boundary_integral_op(sb):
     """sctl_cuda::NearBlocks against the reference's own BoundaryIntegralOp (CPU) on a torus whose near lists are non-empty:
     K_near after "KNearSubtract" (boundary_integral.txx:1165-1240) and the near-field potential of ComputeNearInterac
     (:1311-1385), built from the reference's own near_blk_* / elem_* tables (tests/cpp/test_near_blocks_ref.cpp opens the
-    class's private members); four kernels in FP64, two with trg_normal_dot_prod, two in FP32."""
+    class's private members), and far (sctl_cuda::ParticleDirect) + near against the reference's whole ComputePotential;
+    four kernels in FP64, two with trg_normal_dot_prod, two in FP32."""
     r = _run("test_near_blocks_ref")
     assert r.returncode == 0 and "PASS (0 check(s) failed)" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
