@@ -96,15 +96,15 @@ template <class Real> static double rel_err(const Vector<Real>& a, const Vector<
   return m > 0 ? e / m : e;
 }
 
-template <class Real, class Kernel> static void run(const char* what, bool ndot, double tol) {
+template <class Real, class Kernel> static void run(const char* what, bool ndot, double tol, Long Nu = 64, Long Nv = 32, double dist = 0.2, bool timing = false) {
   constexpr Integer KDIM0 = Kernel::SrcDim(), KDIM1 = Kernel::TrgDim();
   const Integer KDIM1_ = ndot ? KDIM1 / 3 : KDIM1;
-  TorusPatchList<Real> elems(64, 32, (Real)0.2);
+  TorusPatchList<Real> elems(Nu, Nv, (Real)dist);
   Kernel ker;
   BoundaryIntegralOp<Real, Kernel> op(ker, ndot);
   op.SetAccuracy((Real)1e-10);
   op.AddElemList(elems);
-  const Long N = 64 * 32;
+  const Long N = Nu * Nv;
   Vector<Real> F(N * KDIM0), U;
   unsigned long long z = 0x9E3779B97F4A7C15ULL;
   for (auto& f : F) { z ^= z << 13; z ^= z >> 7; z ^= z << 17; f = (Real)((z >> 11) * (1.0 / 9007199254740992.0)) - (Real)0.5; }
@@ -158,12 +158,46 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
       else v = Ufar[i * KDIM1_ + k];
       Utot[i * KDIM1_ + k] = v + Ugpu[i * KDIM1_ + k];
     }
+  if (timing) {  // one apply with a new density: reference (CPU, far + near) against the two sessions (GPU)
+    for (auto& f : F) f = -f;
+    for (Long i = 0; i < N; i++)
+      for (Long j = 0; j < KDIM0; j++) F_far[i * KDIM0 + j] = F[i * KDIM0 + j] * op.wts_far[i];
+    auto t0 = std::chrono::steady_clock::now();
+    op.ComputePotential(U, F);
+    const double t_ref = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    double t_gpu = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+      t0 = std::chrono::steady_clock::now();
+      pd.SetSrcDensity("Src", F_far);
+      pd.Eval(Ufar, "Trg");
+      nb.Apply(U_near, F);
+      op.comm_.ScatterForward(U_near, op.near_scatter_index);
+      for (Long i = 0; i < N; i++)
+        for (Long k = 0; k < KDIM1_; k++) {
+          Real v = Ufar[i * KDIM1_ + k];
+          for (Long j = 0; j < op.near_trg_cnt[i]; j++) v += U_near[(op.near_trg_dsp[i] + j) * KDIM1_ + k];
+          Utot[i * KDIM1_ + k] = v;
+        }
+      t_gpu = std::min(t_gpu, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      U_near.ReInit(Nnear * KDIM1_);
+    }
+    std::printf("%-24s %ld nodes, %ld near pairs, K_near %.2f GB: reference ComputePotential %.4f s on %d host threads, sessions %.4f s per apply (%.0fx)\n", what, (long)N,
+                (long)Nnear, op.K_near.Dim() * sizeof(Real) * 1e-9, t_ref, omp_get_max_threads(), t_gpu, t_ref / t_gpu);
+  }
   const double eT = rel_err(Utot, U);
   CHECK(eT <= tol, "%s: far + near potential differs from the reference's ComputePotential by %.3e", what, eT);
   std::printf("%-44s blocks %5ld  near pairs %7ld  K_near err %.2e  near U err %.2e  ComputePotential err %.2e\n", what, (long)Nblk, (long)Nnear, eK, eU, eT);
 }
 
-int main() {
+int main(int argc, char** argv) {
+  if (argc > 2) {  // timing mode: <exe> Nu Nv [dist_far]
+    const Long Nu = std::atol(argv[1]), Nv = std::atol(argv[2]);
+    const double dist = argc > 3 ? std::atof(argv[3]) : 0.08;
+    run<double, Laplace3D_FxU>("Laplace3D_FxU f64", false, 1e-12, Nu, Nv, dist, true);
+    run<double, Stokes3D_FxU>("Stokes3D_FxU f64", false, 1e-12, Nu, Nv, dist, true);
+    std::printf("%s (%d check(s) failed)\n", n_fail ? "FAIL" : "PASS", n_fail);
+    return n_fail ? 1 : 0;
+  }
   run<double, Laplace3D_FxU>("Laplace3D_FxU f64", false, 1e-12);
   run<double, Laplace3D_DxU>("Laplace3D_DxU f64", false, 1e-12);
   run<double, Stokes3D_FxU>("Stokes3D_FxU f64", false, 1e-12);
