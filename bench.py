@@ -77,10 +77,25 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread this process may
+    run on, so the OpenMP runtime the checker links (libgomp) is told so directly."""
+    import ctypes
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(n)  # read by libgomp if it is not loaded yet
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    except OSError:
+        pass
+    return n
+
+
 def cpu_arm(kernel, N, nsub, steps, warmup, want_result=False, dtype=np.float64, points="cube", log2n=0):
     """The reference's CPU Eval on all N sources x nsub strided targets; returns (pairs/s, info, subset result)."""
     import oracle
     from sctl_b200 import synth
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "TORCHELASTIC_RUN_ID" in os.environ:
+        use_all_host_threads()
     orc = oracle.best_cpu_oracle()
     k0, k1, nd = DIMS[kernel]
     r_src, n_src, v_src, r_trg = synth.cube(N, N, k0, nd, dtype=dtype)
@@ -323,7 +338,6 @@ def main():
     if world > 1 and not args.no_cpu_baseline:
         # multi-GPU runs carry no cpu_baseline (N = 1 only) but still check the gathered result against the CPU reference
         nsub = min(N, 1 << 12)
-        torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))  # torchrun pins OMP_NUM_THREADS=1; the checker shares the OpenMP runtime
         _, info, (idx, cpu_res), _ = cpu_arm(kernel, N, nsub, 1, 1, want_result=True, dtype=npdt, points=args.points, log2n=args.log2n)
         got = full.cpu().numpy().reshape(-1, k1)[idx].reshape(-1)
         line["parity"] = {"max_abs_err_over_vinf": float(np.abs(got.astype(np.float64) - cpu_res.astype(np.float64)).max() / np.abs(full.cpu().numpy()).max()),

@@ -48,3 +48,18 @@ def test_our_arm_surface_points_small():
     d = _run(["--log2n", "14", "--points", "torus", "--steps", "2", "--warmup", "3", "--cpu-targets", "2048", "--no-e2e"])
     assert "torus surface nodes" in d["config"]["workload"] and "targets == sources" in d["config"]["workload"]
     assert d["parity"]["max_abs_err_over_vinf"] <= 1e-12 and d["value"] > 0
+
+
+def test_reference_arm_uses_all_host_threads_under_torchrun():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must still use every host thread it may run on."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", TORCHELASTIC_RUN_ID="test", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--log2n", "13", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads(r.stdout.strip())
+    want = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["cores"] == want and d["n_gpus"] == 2
+    # the other ranks exit 0 without work and print nothing
+    env["RANK"] = "1"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--log2n", "13"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
