@@ -162,6 +162,12 @@ int sctl_cuda_direct_eval(sctl_cuda_direct_t h, int trg, int digits, void* U, in
  *                    is then created with K1 = (kernel target dim) / 3
  *   apply            "EvalNear" (:1324-1340): U_b = K_b * F_b for every block in one launch (overwrites U; blocks
  *                    without sources give zeros, :1327-1331); F and U are host arrays, only they cross PCIe
+ *   set_targets      the tables of ComputeNearInterac's tail (:1366-1381): near_trg_cnt / near_trg_dsp per target and
+ *                    near_scatter_index (one process: ScatterForward is out[p] = in[scatter[p]], comm.txx:1499-1510)
+ *   apply_accumulate "EvalNear" + that tail in one call: U[i*K1+k] += sum_{j < near_trg_cnt[i]}
+ *                    U_near[near_scatter_index[near_trg_dsp[i]+j]*K1+k], j ascending onto what U holds (the reference's
+ *                    order); U has n_trg*K1 values, so per apply F and U go up and U comes down -- U_near (one entry per
+ *                    near PAIR, typically 10x the targets) never leaves the device
  *   get_matrix       download K (tests)
  * All tables are copied at create; all pointers are host pointers; nothing is retained after return. */
 typedef struct sctl_cuda_near_s* sctl_cuda_near_t;
@@ -174,6 +180,9 @@ int sctl_cuda_near_get_matrix(sctl_cuda_near_t h, void* K, int64_t n_reals);
 int sctl_cuda_near_subtract_direct(sctl_cuda_near_t h, int kernel_id, int digits, int64_t Ns, const void* Xs, const void* Xn, const void* wts,
                                    int64_t Nt, const void* Xt, const void* Xn_trg /* NULL, or trg_normal_dot_prod */, const void* ctx, int64_t ctx_bytes);
 int sctl_cuda_near_apply(sctl_cuda_near_t h, const void* F, int64_t nF, void* U, int64_t nU);
+int sctl_cuda_near_set_targets(sctl_cuda_near_t h, int64_t n_trg, const int64_t* near_trg_cnt, const int64_t* near_trg_dsp, int64_t n_near,
+                               const int64_t* near_scatter_index);
+int sctl_cuda_near_apply_accumulate(sctl_cuda_near_t h, const void* F, int64_t nF, void* U /* n_trg*K1, accumulated into */, int64_t nU);
 
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
  *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64;

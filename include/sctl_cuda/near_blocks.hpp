@@ -3,6 +3,7 @@
 //
 //   SubtractDirect   "KNearSubtract"  (reference include/sctl/boundary_integral.txx:1165-1240)
 //   Apply            "EvalNear"       (boundary_integral.txx:1324-1340)
+//   ApplyAccumulate  "EvalNear" + the scatter / per-target accumulation that ends ComputeNearInterac (:1366-1381)
 //
 // The constructor takes BoundaryIntegralOp's own work-list vectors (near_blk_elem / near_blk_t0 / near_blk_cnt,
 // :1009-1032) and per-element tables and flattens them into the per-block table of the C ABI, so a maintainer can
@@ -74,6 +75,23 @@ template <class Real> class NearBlocks {
   // U_near = blockwise K_near * F (overwrites; :1324-1340).  U_near must have near_elem_dsp.back()+near_elem_cnt.back() targets.
   template <class VecOut, class VecIn> void Apply(VecOut& U_near, const VecIn& F) const {
     if (sctl_cuda_near_apply(h_, F.Dim() ? &F[0] : nullptr, F.Dim(), U_near.Dim() ? &U_near[0] : nullptr, U_near.Dim())) detail::die("sctl_cuda_near_apply");
+  }
+
+  // Tables of ComputeNearInterac's tail as BoundaryIntegralOp holds them (Vector<Long>): near_trg_cnt, near_trg_dsp (one per
+  // target of the operator) and near_scatter_index (one per near pair); one-process Comm (ScatterForward is a local gather).
+  template <class LongVec> void SetTargets(const LongVec& near_trg_cnt, const LongVec& near_trg_dsp, const LongVec& near_scatter_index) {
+    const Long n = near_trg_cnt.Dim(), m = near_scatter_index.Dim();
+    SCTL_CUDA_ASSERT(near_trg_dsp.Dim() == n);
+    std::vector<int64_t> cnt(n), dsp(n), sc(m);
+    for (Long i = 0; i < n; i++) { cnt[i] = near_trg_cnt[i]; dsp[i] = near_trg_dsp[i]; }
+    for (Long i = 0; i < m; i++) sc[i] = near_scatter_index[i];
+    if (sctl_cuda_near_set_targets(h_, n, cnt.data(), dsp.data(), m, sc.data())) detail::die("sctl_cuda_near_set_targets");
+  }
+
+  // U += near-field correction, exactly the loops at :1324-1340 and :1366-1381 (U must already have Ntrg*KDIM1_ values, e.g.
+  // the far field); only F and U cross PCIe.
+  template <class VecOut, class VecIn> void ApplyAccumulate(VecOut& U, const VecIn& F) const {
+    if (sctl_cuda_near_apply_accumulate(h_, F.Dim() ? &F[0] : nullptr, F.Dim(), U.Dim() ? &U[0] : nullptr, U.Dim())) detail::die("sctl_cuda_near_apply_accumulate");
   }
 
  private:

@@ -5,6 +5,8 @@ Follows the reference loops in include/sctl/boundary_integral.txx:
     (element lists whose FarFieldDensityOperatorTranspose is the identity): Mker = KernelMatrix(Xtrg_near_, X, Xn)
     (:1196-1197), rows scaled by wts[s] (:1198-1205), K_near_[i][j] -= Mker[j][i] (:1219-1229);
   * near_apply     "EvalNear" (:1324-1340): U_ = K_near_ * F_ per block; blocks without sources give zeros (:1327-1331).
+  * near_accumulate  the tail of ComputeNearInterac (:1366-1381): ScatterForward on one process (comm.txx:1499-1510,
+    out[p] = in[scatter[p]]) and U[i] += the near_trg_cnt[i] entries from near_trg_dsp[i] on, j ascending.
 KernelMatrix itself comes from the oracle object passed in (the C port or the unmodified reference), which is pinned.
 PINNING: the block loops act on private state of BoundaryIntegralOp (K_near, near_blk_*), so this numpy restatement is
 not run against the reference directly; the same device code that it checks is pinned against the reference's own
@@ -53,4 +55,15 @@ def near_apply(k0, k1, tab, K, F, nU, dtype=np.float64):
             continue
         blk = K[k_dsp[b]:k_dsp[b] + rows * cols].reshape(rows, cols)
         U[u_dsp[b] * k1:u_dsp[b] * k1 + rows] = blk @ F[f_dsp[b] * k0:f_dsp[b] * k0 + cols]
+    return U
+
+
+def near_accumulate(k1, U, U_near, near_trg_cnt, near_trg_dsp, near_scatter_index):
+    """U (n_trg*k1, changed in place and returned) += scattered U_near, in the reference's order (sequential adds per target)."""
+    U_near = np.asarray(U_near).reshape(-1, k1)
+    scattered = U_near[np.asarray(near_scatter_index, dtype=np.int64)]  # ScatterForward, npes == 1
+    Uv = U.reshape(-1, k1)
+    for i in range(Uv.shape[0]):
+        for j in range(int(near_trg_cnt[i])):
+            Uv[i] += scattered[int(near_trg_dsp[i]) + j]
     return U

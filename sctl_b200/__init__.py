@@ -70,6 +70,8 @@ def load_library():
     L.sctl_cuda_near_get_matrix.argtypes = [vp, vp, i64]
     L.sctl_cuda_near_subtract_direct.argtypes = [vp, i, i, i64, vp, vp, vp, i64, vp, vp, vp, i64]
     L.sctl_cuda_near_apply.argtypes = [vp, vp, i64, vp, i64]
+    L.sctl_cuda_near_set_targets.argtypes = [vp, i64, p64, p64, i64, p64]
+    L.sctl_cuda_near_apply_accumulate.argtypes = [vp, vp, i64, vp, i64]
     L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
     _lib = L
     return L
@@ -518,4 +520,21 @@ class NearBlocks:
         if U is None or U.size < self.nU or U.dtype != self._dtype or not U.flags.c_contiguous:
             U = np.zeros(self.nU, dtype=self._dtype)
         _check(load_library().sctl_cuda_near_apply(self._h, _np_ptr(F), F.size, _np_ptr(U.reshape(-1)), U.size))
+        return U
+
+    def set_targets(self, near_trg_cnt, near_trg_dsp, near_scatter_index):
+        """Tables of ComputeNearInterac's tail (boundary_integral.txx:1366-1381), one-process ``Comm``."""
+        cnt, dsp, sc = [np.ascontiguousarray(a, dtype=np.int64).reshape(-1) for a in (near_trg_cnt, near_trg_dsp, near_scatter_index)]
+        if cnt.size != dsp.size:
+            raise SctlCudaError("near_trg_cnt and near_trg_dsp differ in length")
+        p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        _check(load_library().sctl_cuda_near_set_targets(self._h, cnt.size, p64(cnt), p64(dsp), sc.size, p64(sc)))
+        self.n_trg = int(cnt.size)
+
+    def apply_accumulate(self, F, U):
+        """``U += `` the near-field correction ("EvalNear" + scatter + per-target accumulation); ``U`` is changed in place."""
+        F = np.ascontiguousarray(F, dtype=self._dtype).reshape(-1)
+        if not isinstance(U, np.ndarray) or U.dtype != self._dtype or not U.flags.c_contiguous:
+            raise SctlCudaError("U must be a contiguous %s array (it is accumulated into)" % np.dtype(self._dtype).name)
+        _check(load_library().sctl_cuda_near_apply_accumulate(self._h, _np_ptr(F), F.size, _np_ptr(U.reshape(-1)), U.size))
         return U

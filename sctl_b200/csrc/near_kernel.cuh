@@ -173,4 +173,25 @@ __global__ void __launch_bounds__(32 * NEAR_APPLY_WARPS, (sizeof(Real) == 8 ? 5 
   }
 }
 
+// Tail of ComputeNearInterac (boundary_integral.txx:1366-1381): comm_.ScatterForward(U_near, near_scatter_index)
+// (one process: out[p] = in[scatter[p]], comm.txx:1499-1510) followed by
+//   for j < near_trg_cnt[i]:  U[i*K1+k] += U_near_scattered[(near_trg_dsp[i]+j)*K1+k]
+// fused into one gather: a thread owns one (target, component) of U and adds its near contributions in the reference's
+// order (j ascending, onto the value U already holds), so the result does not depend on the launch geometry.
+// HBM bound: per near pair one 8-byte index and K1 Reals read at scattered addresses; U read and written once.
+template <class Real>
+__global__ void __launch_bounds__(256) near_gather_accumulate_kernel(int64_t n_trg, int K1, const int64_t* __restrict__ cnt, const int64_t* __restrict__ dsp,
+                                                                      const int64_t* __restrict__ scatter, const Real* __restrict__ U_near, Real* __restrict__ U) {
+  const int64_t n = n_trg * K1;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / K1;
+    const int k = (int)(idx - i * K1);
+    const int64_t c = cnt[i];
+    const int64_t* sp = scatter + dsp[i];
+    Real u = U[idx];
+    for (int64_t j = 0; j < c; j++) u += U_near[sp[j] * K1 + k];
+    U[idx] = u;
+  }
+}
+
 }  // namespace sctl_cuda

@@ -136,6 +136,15 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
   op.ComputeNearInterac(Uref, F);
   const double eU = rel_err(Ugpu, Uref);
   CHECK(eU <= tol, "%s: near-field potential differs from the reference's ComputeNearInterac by %.3e", what, eU);
+  // the same tail on the device (ApplyAccumulate = EvalNear + ScatterForward + per-target accumulation): bit-identical to the
+  // host loops above, which add in the same order
+  nb.SetTargets(op.near_trg_cnt, op.near_trg_dsp, op.near_scatter_index);
+  Vector<Real> Uacc(N * KDIM1_);
+  Uacc.SetZero();
+  nb.ApplyAccumulate(Uacc, F);
+  Long n_diff = 0;
+  for (Long i = 0; i < Uacc.Dim(); i++) n_diff += (Uacc[i] != Ugpu[i]);
+  CHECK(n_diff == 0, "%s: ApplyAccumulate differs from Apply + the reference's host tail in %ld entries", what, (long)n_diff);
   // 3. the whole apply from the two sessions (INTEGRATION.md 3a + 3b): far field through the device-resident evaluator with
   //    the reference's far-field nodes and F * wts (ComputeFarField, :1248-1309), plus the near correction above, against
   //    the reference's ComputePotential (far + near, all on the CPU)
@@ -170,16 +179,9 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
       t0 = std::chrono::steady_clock::now();
       pd.SetSrcDensity("Src", F_far);
       pd.Eval(Ufar, "Trg");
-      nb.Apply(U_near, F);
-      op.comm_.ScatterForward(U_near, op.near_scatter_index);
-      for (Long i = 0; i < N; i++)
-        for (Long k = 0; k < KDIM1_; k++) {
-          Real v = Ufar[i * KDIM1_ + k];
-          for (Long j = 0; j < op.near_trg_cnt[i]; j++) v += U_near[(op.near_trg_dsp[i] + j) * KDIM1_ + k];
-          Utot[i * KDIM1_ + k] = v;
-        }
+      nb.ApplyAccumulate(Ufar, F);  // far field + near correction; only F and U cross PCIe
       t_gpu = std::min(t_gpu, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-      U_near.ReInit(Nnear * KDIM1_);
+      Utot = Ufar;
     }
     std::printf("%-24s %ld nodes, %ld near pairs, K_near %.2f GB: reference ComputePotential %.4f s on %d host threads, sessions %.4f s per apply (%.0fx)\n", what, (long)N,
                 (long)Nnear, op.K_near.Dim() * sizeof(Real) * 1e-9, t_ref, omp_get_max_threads(), t_gpu, t_ref / t_gpu);

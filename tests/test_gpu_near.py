@@ -120,3 +120,61 @@ def test_near_blocks_trg_normal_dot_prod(sb, cpu_oracle, kernel, dtype):
     nb.close()
     with pytest.raises(sb.SctlCudaError, match="multiple of 3"):
         sb.NearBlocks(sb.Laplace3D_FxU, *tab, dtype=dtype, trg_normal_dot_prod=True)
+
+
+def near_target_tables(n_trg_op, n_near, seed):
+    """near_trg_cnt / near_trg_dsp / near_scatter_index with the reference's structure (BuildNearList,
+    boundary_integral.txx:490-520): the scatter index permutes the near pairs so that each target's contributions become
+    contiguous; targets without near elements have count 0 and offset 0 (:507-509)."""
+    rng = np.random.RandomState(seed)
+    owner = rng.randint(0, n_trg_op, size=n_near)          # operator target of every near pair (element-major order)
+    owner[rng.rand(n_near) < 0.1] = 3                      # one target with many contributions
+    scatter = np.argsort(owner, kind="stable").astype(np.int64)
+    cnt = np.bincount(owner, minlength=n_trg_op).astype(np.int64)
+    dsp = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.int64)
+    dsp[cnt == 0] = 0
+    return cnt, dsp, scatter
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel", ["Laplace3D_FxU", "Stokes3D_FxU"])
+def test_near_apply_accumulate_matches_the_reference_tail(sb, kernel, dtype):
+    """apply_accumulate = EvalNear + ScatterForward + per-target accumulation (boundary_integral.txx:1324-1340,1366-1381):
+    bit-identical to the host tail applied to the session's own U_near (same order of additions)."""
+    from oracle import near_blocks as nbo
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    tab, n_nodes, n_far, n_near, K_len = block_list(40, k0, k1, seed=5)
+    n_trg_op = 517
+    cnt, dsp, scatter = near_target_tables(n_trg_op, n_near, seed=9)
+    nb = sb.NearBlocks(sb.KERNELS[kernel], *tab, dtype=dtype)
+    K0_ = (synth.splitmix_u01(22, K_len) - 0.5).astype(dtype)
+    F = (synth.splitmix_u01(23, n_nodes * k0) - 0.5).astype(dtype)
+    U0 = (synth.splitmix_u01(24, n_trg_op * k1) - 0.5).astype(dtype)   # e.g. the far field
+    with pytest.raises(sb.SctlCudaError, match="no matrix"):
+        nb.apply_accumulate(F, U0.copy())
+    nb.set_matrix(K0_)
+    with pytest.raises(sb.SctlCudaError, match="no target tables"):
+        nb.apply_accumulate(F, U0.copy())
+    nb.set_targets(cnt, dsp, scatter)
+    U_near = nb.apply(F)
+    want = nbo.near_accumulate(k1, U0.copy(), U_near, cnt, dsp, scatter)
+    got = nb.apply_accumulate(F, U0.copy())
+    assert np.array_equal(got, want)
+    # and against the numpy restatement of the whole thing
+    want64 = nbo.near_accumulate(k1, U0.astype(np.float64), nbo.near_apply(k0, k1, tab, K0_.astype(np.float64), F.astype(np.float64), n_near * k1), cnt, dsp, scatter)
+    assert rel_err(got, want64) <= (1e-13 if dtype == np.float64 else TOL[dtype])
+    # accumulates: a second call adds the same correction again; wrong sizes and bad tables are refused
+    twice = nb.apply_accumulate(F, got.copy())
+    assert rel_err(twice - got, want64 - U0.astype(np.float64)) <= (1e-12 if dtype == np.float64 else 1e-4)
+    with pytest.raises(sb.SctlCudaError, match="U has"):
+        nb.apply_accumulate(F, np.zeros(n_trg_op * k1 + 1, dtype=dtype))
+    bad = scatter.copy()
+    bad[0] = n_near
+    with pytest.raises(sb.SctlCudaError, match="scatter index"):
+        nb.set_targets(cnt, dsp, bad)
+    with pytest.raises(sb.SctlCudaError, match="near range"):
+        nb.set_targets(cnt + 1, dsp, scatter)
+    # plain apply still works after the tables were (re)set
+    assert np.array_equal(nb.apply(F), U_near)
+    nb.close()

@@ -148,3 +148,16 @@ def test_splitmix_matches_c_generator(port):
     from sctl_b200 import synth
     for seed, n, first in ((1, 1000, 0), (4, 257, 12345)):
         assert np.array_equal(synth.splitmix_u01(seed, n, first), port.splitmix(seed, n, first=first))
+
+
+def test_near_accumulate_restatement_small():
+    """oracle/near_blocks.near_accumulate against a hand-worked case of ComputeNearInterac's tail
+    (boundary_integral.txx:1366-1381; ScatterForward on one process is out[p] = in[scatter[p]], comm.txx:1499-1510)."""
+    from oracle import near_blocks as nbo
+    U_near = np.array([10.0, 20.0, 30.0, 40.0])          # one value per near pair, element-major
+    scatter = np.array([2, 0, 3, 1])                      # scattered = [30, 10, 40, 20]
+    cnt, dsp = np.array([1, 0, 3]), np.array([0, 0, 1])   # target 0 <- {30}; target 1 <- {}; target 2 <- {10, 40, 20}
+    U = nbo.near_accumulate(1, np.array([1.0, 2.0, 3.0]), U_near, cnt, dsp, scatter)
+    assert U.tolist() == [31.0, 2.0, 73.0]
+    U = nbo.near_accumulate(2, np.zeros(4), np.arange(8.0), np.array([2, 0]), np.array([0, 0]), np.array([3, 1, 0, 2]))
+    assert U.tolist() == [6 + 2, 7 + 3, 0, 0]
