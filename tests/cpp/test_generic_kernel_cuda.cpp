@@ -4,12 +4,14 @@
 // but through the GPU path.  Needs a B200; compiled by __graft_entry__.build(), run by tests/test_gpu_cpp.py.
 #include <cmath>
 #include <cstdio>
+#include <memory>
 #include <string>
 #include <vector>
 #include <algorithm>
 
 #include "sctl_cuda/generic_kernel.hpp"
 #include "sctl_cuda/mini_containers.hpp"
+#include "sctl_cuda/bio_apply.hpp"
 #include "sctl_cuda/near_blocks.hpp"
 #include "sctl_cuda/particle_direct.hpp"
 
@@ -199,7 +201,8 @@ template <class R> static void session_layers() {
       for (Long t0 = 0; t0 < near_elem_cnt[e]; t0 += 64) { be.push_back(e); bt.push_back(t0); bc.push_back(std::min<Long>(64, near_elem_cnt[e] - t0)); }
     LV blk_e((Long)be.size()), blk_t((Long)be.size()), blk_c((Long)be.size());
     for (size_t i = 0; i < be.size(); i++) { blk_e[i] = be[i]; blk_t[i] = bt[i]; blk_c[i] = bc[i]; }
-    sctl_cuda::NearBlocks<R> nb(3, 3, blk_e, blk_t, blk_c, elem_nds_cnt, elem_nds_dsp, elem_nds_dsp, near_elem_dsp, K_near_dsp);
+    std::unique_ptr<sctl_cuda::NearBlocks<R>> nbp(new sctl_cuda::NearBlocks<R>(3, 3, blk_e, blk_t, blk_c, elem_nds_cnt, elem_nds_dsp, elem_nds_dsp, near_elem_dsp, K_near_dsp));
+    sctl_cuda::NearBlocks<R>& nb = *nbp;
     const Long K_len = (300 * 200 + 400 * 250) * 9;
     Vector<R> K(K_len), K2(K_len), Unear(450 * 3);
     for (Long i = 0; i < K_len; i++) K[i] = rnd();
@@ -228,6 +231,29 @@ template <class R> static void session_layers() {
     }
     CHECK(err <= tol * mag);
     CHECK(uerr <= (sizeof(R) == 8 ? (R)1e-12 : (R)1e-4) * umag);
+    // bio_apply.hpp: far field (F * wts through the resident evaluator) + near correction (ApplyAccumulate) behind one call.
+    // Every near pair belongs to its own operator target here; the scatter index reverses their order.
+    LV cnt(Nt), dsp(Nt), sc(Nt);
+    for (Long i = 0; i < Nt; i++) { cnt[i] = 1; dsp[i] = i; sc[i] = Nt - 1 - i; }
+    nb.SetTargets(cnt, dsp, sc);
+    Vector<R> FW(Ns * 3), Ufar, Ubio, none;
+    for (Long i = 0; i < Ns * 3; i++) FW[i] = F[i] * W[i / 3];
+    sl.template Eval<R, true>(Ufar, Xt, Xs, none, FW);
+    sctl_cuda::BioApply<R> bio(sl, false, -1, Xs, Xn, W, Xt, none);
+    CHECK(bio.SrcCount() == Ns && bio.TrgCount() == Nt && bio.TrgDof() == 3);
+    bio.ComputePotential(Ubio, F);  // far field alone while no near session is attached
+    R e0 = 0, e1 = 0, m1 = 0;
+    for (Long i = 0; i < Nt * 3; i++) e0 = std::fmax(e0, std::fabs(Ubio[i] - Ufar[i]));
+    bio.SetNear(std::move(nbp));
+    bio.ComputePotential(Ubio, F);
+    for (Long i = 0; i < Nt; i++)
+      for (Long k = 0; k < 3; k++) {
+        const R want = Ufar[i * 3 + k] + Unear[(Nt - 1 - i) * 3 + k];
+        e1 = std::fmax(e1, std::fabs(Ubio[i * 3 + k] - want));
+        m1 = std::fmax(m1, std::fabs(want));
+      }
+    CHECK(e0 <= tol * m1);
+    CHECK(e1 <= tol * m1);
   }
 }
 

@@ -9,7 +9,9 @@
 //      part from a zero matrix and compares with the reference's K_near;
 //   2. applies it on the GPU, runs the reference's own scatter / accumulate tail (:1371-1383) on the result and compares
 //      with the reference's ComputeNearInterac.
-//   3. adds the far field from sctl_cuda::ParticleDirect and compares the sum with the reference's ComputePotential.
+//   3. adds the far field from sctl_cuda::ParticleDirect and compares the sum with the reference's ComputePotential;
+//   4. hands the near session to sctl_cuda::BioApply (far field + near correction behind one ComputePotential) and compares
+//      that with the reference's ComputePotential too; the timing mode times this object.
 // Both with and without trg_normal_dot_prod.  Built only where /root/reference is mounted; the binary travels.
 #include <algorithm>
 #include <chrono>
@@ -32,8 +34,7 @@
 #undef private
 #undef protected
 
-#include "sctl_cuda/near_blocks.hpp"
-#include "sctl_cuda/particle_direct.hpp"
+#include "sctl_cuda/bio_apply.hpp"
 
 using namespace sctl;
 
@@ -114,8 +115,9 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
   const Long Nnear = Nelem ? op.near_elem_dsp[Nelem - 1] + op.near_elem_cnt[Nelem - 1] : 0;
   CHECK(Nblk > 0 && Nnear > N, "%s: near list unexpectedly small (blocks %ld, near pairs %ld)", what, (long)Nblk, (long)Nnear);
 
-  sctl_cuda::NearBlocks<Real> nb(KDIM0, KDIM1_, op.near_blk_elem, op.near_blk_t0, op.near_blk_cnt, op.elem_nds_cnt, op.elem_nds_dsp, op.elem_nds_dsp_far, op.near_elem_dsp,
-                                 op.K_near_dsp);
+  std::unique_ptr<sctl_cuda::NearBlocks<Real>> nbp(new sctl_cuda::NearBlocks<Real>(KDIM0, KDIM1_, op.near_blk_elem, op.near_blk_t0, op.near_blk_cnt, op.elem_nds_cnt, op.elem_nds_dsp,
+                                                                                    op.elem_nds_dsp_far, op.near_elem_dsp, op.K_near_dsp));
+  sctl_cuda::NearBlocks<Real>& nb = *nbp;
   Vector<Real> Kzero(op.K_near.Dim()), Kgpu(op.K_near.Dim());
   Kzero.SetZero();
   nb.SetMatrix(Kzero);
@@ -167,28 +169,30 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
       else v = Ufar[i * KDIM1_ + k];
       Utot[i * KDIM1_ + k] = v + Ugpu[i * KDIM1_ + k];
     }
-  if (timing) {  // one apply with a new density: reference (CPU, far + near) against the two sessions (GPU)
+  // 4. the same through one object
+  sctl_cuda::BioApply<Real> bio(ker, ndot, 11, op.X_far, op.Xn_far, op.wts_far, op.Xtrg, op.Xn_trg);
+  bio.SetNear(std::move(nbp));
+  Vector<Real> Ubio;
+  bio.ComputePotential(Ubio, F);
+  const double eB = rel_err(Ubio, U);
+  CHECK(eB <= tol, "%s: BioApply::ComputePotential differs from the reference's ComputePotential by %.3e", what, eB);
+  if (timing) {  // one apply with a new density: reference (CPU, far + near) against BioApply (GPU)
     for (auto& f : F) f = -f;
-    for (Long i = 0; i < N; i++)
-      for (Long j = 0; j < KDIM0; j++) F_far[i * KDIM0 + j] = F[i * KDIM0 + j] * op.wts_far[i];
     auto t0 = std::chrono::steady_clock::now();
     op.ComputePotential(U, F);
     const double t_ref = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     double t_gpu = 1e30;
     for (int rep = 0; rep < 3; rep++) {
       t0 = std::chrono::steady_clock::now();
-      pd.SetSrcDensity("Src", F_far);
-      pd.Eval(Ufar, "Trg");
-      nb.ApplyAccumulate(Ufar, F);  // far field + near correction; only F and U cross PCIe
+      bio.ComputePotential(Utot, F);  // F * wts, far field, near correction; only F and U cross PCIe
       t_gpu = std::min(t_gpu, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-      Utot = Ufar;
     }
-    std::printf("%-24s %ld nodes, %ld near pairs, K_near %.2f GB: reference ComputePotential %.4f s on %d host threads, sessions %.4f s per apply (%.0fx)\n", what, (long)N,
+    std::printf("%-24s %ld nodes, %ld near pairs, K_near %.2f GB: reference ComputePotential %.4f s on %d host threads, BioApply %.4f s per apply (%.0fx)\n", what, (long)N,
                 (long)Nnear, op.K_near.Dim() * sizeof(Real) * 1e-9, t_ref, omp_get_max_threads(), t_gpu, t_ref / t_gpu);
   }
   const double eT = rel_err(Utot, U);
   CHECK(eT <= tol, "%s: far + near potential differs from the reference's ComputePotential by %.3e", what, eT);
-  std::printf("%-44s blocks %5ld  near pairs %7ld  K_near err %.2e  near U err %.2e  ComputePotential err %.2e\n", what, (long)Nblk, (long)Nnear, eK, eU, eT);
+  std::printf("%-44s blocks %5ld  near pairs %7ld  K_near err %.2e  near U err %.2e  ComputePotential err %.2e  BioApply err %.2e\n", what, (long)Nblk, (long)Nnear, eK, eU, eT, eB);
 }
 
 int main(int argc, char** argv) {

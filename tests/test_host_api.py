@@ -134,7 +134,7 @@ def test_precondition_violations_raise(sbm):
 def test_cpp_host_layer_compiles_standalone(tmp_path):
     """include/sctl_cuda/*.hpp is self-contained C++17 (no SCTL, no CUDA headers needed by callers)."""
     src = tmp_path / "t.cpp"
-    src.write_text('#include "sctl_cuda/generic_kernel.hpp"\n#include "sctl_cuda/mini_containers.hpp"\n'
+    src.write_text('#include "sctl_cuda/generic_kernel.hpp"\n#include "sctl_cuda/mini_containers.hpp"\n#include "sctl_cuda/bio_apply.hpp"\n'
                    "int main(){ sctl_cuda::Stokes3D_FxU K; static_assert(decltype(K)::SrcDim()==3 && decltype(K)::TrgDim()==3 && decltype(K)::NormalDim()==0, \"dims\");\n"
                    " return (K.Name()==\"Stokes3D-FxU\" && K.FLOPS()==23) ? 0 : 1; }\n")
     exe = tmp_path / "t"
