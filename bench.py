@@ -77,6 +77,15 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(load)), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback of /opt/skills/guides/B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
 def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host thread this process may
     run on, so the OpenMP runtime the checker links (libgomp) is told so directly."""
@@ -319,6 +328,13 @@ def main():
                 "pairs_per_step": my_pairs, "flop_per_pair": F_ALG[kernel],
                 "frac_sctl_flops_convention": my_pairs * SCTL_FLOPS[kernel] / (k_ms * 1e-3) * 1e-12 / peak_sustained,
                 "fp_instr_per_pair": FP_INSTR[kernel], "pipe_ceiling_frac": F_ALG[kernel] / (2.0 * FP_INSTR[kernel])}
+    if traffic is not None and const_path:
+        # the contract's HBM view of the same kernel, to show that it is not the binding roof: DRAM bytes of one pair-kernel
+        # launch (ncu) x launches per step / kernel time, against the measured copy bandwidth
+        hbm_peak, hbm_src = hbm_peak_gbs()
+        gbs = traffic * pair_launches / (k_ms * 1e-3) * 1e-9
+        roofline["hbm_view"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
+                                "note": "targets and v_trg are re-read once per source chunk (%d launches per step); at %.1f %% of the HBM roof the kernel is not memory-bound" % (pair_launches, 100 * gbs / hbm_peak)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(res_ms) / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.real, "data": "synthetic", "config": config, "clocks": clocks,
