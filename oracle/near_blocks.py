@@ -11,7 +11,9 @@ KernelMatrix itself comes from the oracle object passed in (the C port or the un
 PINNING: the block loops act on private state of BoundaryIntegralOp (K_near, near_blk_*), so this numpy restatement is
 not run against the reference directly; the same device code that it checks is pinned against the reference's own
 BoundaryIntegralOp by tests/cpp/test_near_blocks_ref.cpp (private members opened in that test TU, K_near and
-ComputeNearInterac compared on a torus with non-empty near lists, with and without trg_normal_dot_prod).
+ComputeNearInterac compared on a torus with non-empty near lists, with and without trg_normal_dot_prod).  near_accumulate
+is checked on a hand-worked case (tests/test_oracle.py) and the device code it checks is compared entry by entry with the
+reference's own ScatterForward + accumulation loops in that same C++ test (bit-identical), and with ComputeNearInterac.
 Block table columns as in include/sctl_cuda.h (f_dsp, far_dsp, ns, u_dsp, nt, k_dsp)."""
 import numpy as np
 
