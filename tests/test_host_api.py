@@ -170,3 +170,35 @@ def test_sass_evidence_of_the_b200_design(sbm):
         assert id(body) in helmholtz or len(re.findall(r" LDC(\.\d+)? R\d+, c\[0x3\]", body)) <= 2
         assert len(re.findall(r"[DF](FMA|MUL|ADD) [^;]*UR\d+", body)) >= 40
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", sbm.LIB_PATH], capture_output=True, text=True).stdout
+
+
+def test_planners_hold_their_invariants_on_random_sizes(sbm):
+    """Property test (hypothesis) of the two pieces of host logic that decide how sources are cut: whatever the sizes, chunks
+    tile the sources exactly (no source dropped or counted twice, no empty chunk) and the constant-bank layout stays inside
+    its slice of the 64 KB bank."""
+    from hypothesis import given, settings, strategies as st
+
+    sizes = st.one_of(st.integers(1, 5000), st.integers(1, 1 << 24))
+
+    @settings(max_examples=300, deadline=None)
+    @given(Ns=sizes, Nt=sizes, tpb=st.sampled_from([32, 256, 512, 1024, 2048]), slots=st.sampled_from([148, 296, 592]),
+           min_tiles=st.integers(1, 8), max_split=st.sampled_from([1, 8, 64, 1024]))
+    def ring(Ns, Nt, tpb, slots, min_tiles, max_split):
+        p = sbm.plan_eval(Ns, Nt, tpb, slots, 256 * min_tiles, max_split)
+        assert p["n_tblocks"] == -(-Nt // tpb)
+        assert 1 <= p["n_split"] <= max_split and p["chunk"] >= 1
+        assert p["n_split"] * p["chunk"] >= Ns > (p["n_split"] - 1) * p["chunk"]
+        assert 0.0 < p["wave_eff"] <= 1.0 + 1e-12
+
+    @settings(max_examples=300, deadline=None)
+    @given(Ns=sizes, Nt=sizes, rb=st.sampled_from([8, 4]), banks=st.integers(1, 4),
+           kernel=st.sampled_from(["Laplace3D_FxU", "Laplace3D_DxU", "Stokes3D_FxU", "Stokes3D_DxU", "Stokes3D_FxT", "Helmholtz3D_DxU"]))
+    def bank(Ns, Nt, rb, banks, kernel):
+        g = sbm.const_geometry(kernel, rb, Ns, Nt, banks)
+        assert 1 <= g["banks"] <= banks and g["banks"] * g["bank_stride"] <= 63 * 1024 and g["bank_stride"] % 16 == 0
+        assert g["chunk"] >= 1 and g["seg_bytes"] == g["chunk"] * g["rec_bytes"] + g["row_words"] * 4 <= g["bank_stride"]
+        assert g["n_chunks"] * g["chunk"] >= Ns > (g["n_chunks"] - 1) * g["chunk"]
+        assert g["row_words"] == 0 or g["row_words"] * 32 >= -(-Nt // 512)
+
+    ring()
+    bank()
