@@ -128,7 +128,7 @@ int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes,
  * BoundaryIntegralOp::ComputeFarField, boundary_integral.txx:1286-1305): source and target coordinates are uploaded
  * once and stay in HBM, an apply ships only the density in and the potential out.  Sources and targets are
  * addressed by small non-negative slot numbers chosen by the caller (the C++ mirror maps ParticleFMM's names to
- * them).  With n_gpus > 1 the targets are sharded by contiguous block over GPUs 0..n_gpus-1 (the rule of
+ * them).  With n_gpus > 1 the targets are sharded by contiguous block over the session's GPUs (the rule of
  * fmm-wrapper.txx:568) and every GPU holds all sources; no reduction between GPUs (results agree to rounding
  * for any n_gpus: a shard may split the sources differently from the whole target set).
  *   set_src_coord    ParticleFMM::SetSrcCoord(name, X, Xn)   (fmm-wrapper.hpp:166)  normal_dim 0 or 3
@@ -139,7 +139,13 @@ int sctl_cuda_last_plan(int* grid_x, int* grid_y, int* threads, int* smem_bytes,
  *                    source slot that has a kernel into `trg` (fmm-wrapper.txx:562-563,598-619); digits as in Eval.
  * All pointers are host pointers; nothing is retained after return.  A session serialises its own calls. */
 typedef struct sctl_cuda_direct_s* sctl_cuda_direct_t;
-int sctl_cuda_direct_create(int real_bytes, int n_gpus /* 0 or 1: the first GPU */, sctl_cuda_direct_t* out);
+/* n_gpus 0 or 1: the session lives on the device that is CURRENT on the creating thread (with one rank per GPU --
+ * torchrun, MPI -- every rank's far field stays on its own GPU, like sctl_cuda_eval and the near-field session);
+ * n_gpus > 1: devices 0..n_gpus-1.  create_on takes the device ordinals explicitly (distinct, visible). */
+int sctl_cuda_direct_create(int real_bytes, int n_gpus, sctl_cuda_direct_t* out);
+int sctl_cuda_direct_create_on(int real_bytes, int n_gpus, const int* devices, sctl_cuda_direct_t* out);
+/* The session's GPUs: count and (up to `cap`) CUDA device ordinals; either pointer may be NULL. */
+int sctl_cuda_direct_devices(sctl_cuda_direct_t h, int* n_gpus, int* devices, int cap);
 int sctl_cuda_direct_destroy(sctl_cuda_direct_t h);
 int sctl_cuda_direct_set_src_coord(sctl_cuda_direct_t h, int src, int64_t Ns, const void* X, const void* Xn, int normal_dim);
 int sctl_cuda_direct_set_src_density(sctl_cuda_direct_t h, int src, int64_t n_reals, const void* F);

@@ -12,11 +12,19 @@
 //
 // Differences from ParticleFMM: no Comm (one process drives n_gpus GPUs of the node), no periodicity, no PVFMM; the
 // FMM translation kernels given to SetKernels/AddSrc/AddTrg are accepted and ignored except for their dimensions.
+// Devices: ParticleDirect(1) lives on the device that is current on the constructing thread (one rank per GPU: every
+// rank's evaluator stays on the rank's own GPU); ParticleDirect(n > 1) takes devices 0..n-1; ParticleDirect(devices)
+// takes an explicit list.
+// Kernel context (the Helmholtz wavenumber): like the reference, which copies the kernel object with its ctx_ptr
+// (fmm-wrapper.txx:442-443) and dereferences the pointer at every Eval, the pointer given to SetKernelS2T is kept and
+// read again at every EvalDirect -- changing the wavenumber between two evaluations takes effect without a new
+// SetKernelS2T.  The pointee must therefore outlive the interaction, exactly as for ParticleFMM.
 #ifndef SCTL_CUDA_PARTICLE_DIRECT_HPP_
 #define SCTL_CUDA_PARTICLE_DIRECT_HPP_
 
 #include <map>
 #include <string>
+#include <vector>
 
 #include "generic_kernel.hpp"
 
@@ -43,6 +51,9 @@ template <class Real, Integer DIM = 3> class ParticleDirect {
   explicit ParticleDirect(int n_gpus = 1) : h_(nullptr), digits_(10) {  // default accuracy: fmm-wrapper.txx:205
     if (sctl_cuda_direct_create(detail::real_bytes<Real>::value, n_gpus, &h_)) detail::die("sctl_cuda_direct_create");
   }
+  explicit ParticleDirect(const std::vector<int>& devices) : h_(nullptr), digits_(10) {
+    if (sctl_cuda_direct_create_on(detail::real_bytes<Real>::value, (int)devices.size(), devices.data(), &h_)) detail::die("sctl_cuda_direct_create_on");
+  }
   ~ParticleDirect() { sctl_cuda_direct_destroy(h_); }
 
   void SetAccuracy(Integer digits) { digits_ = digits; }
@@ -51,12 +62,12 @@ template <class Real, Integer DIM = 3> class ParticleDirect {
 
   template <class KerS2M, class KerS2L> void AddSrc(const std::string& name, const KerS2M&, const KerS2L&) {
     SCTL_CUDA_ASSERT(src_.find(name) == src_.end());  // "Source name already exists." (fmm-wrapper.txx)
-    src_[name] = next_src_++;
+    src_[name] = take_slot(free_src_, next_src_);
   }
   template <class KerM2T, class KerL2T> void AddTrg(const std::string& name, const KerM2T&, const KerL2T&) {
     SCTL_CUDA_ASSERT(trg_.find(name) == trg_.end());
     Trg t;
-    t.slot = next_trg_++;
+    t.slot = take_slot(free_trg_, next_trg_);
     t.dim = KerM2T::TrgDim();
     t.Nt = 0;
     trg_[name] = t;
@@ -68,21 +79,38 @@ template <class Real, Integer DIM = 3> class ParticleDirect {
     SCTL_CUDA_ASSERT(KerS2T::TrgDim() == trg_[trg_name].dim);  // CheckKernelDims (fmm-wrapper.txx:627-)
     const int id = detail::kernel_id_from_name(KerS2T::Name());
     SCTL_CUDA_ASSERT(id >= 0);
-    const void* ctx = ker_s2t.GetCtxPtr();
-    if (sctl_cuda_direct_set_kernel_s2t(h_, src_[src_name], trg_[trg_name].slot, id, ctx, ctx ? (int64_t)sizeof(Real) : 0)) detail::die("sctl_cuda_direct_set_kernel_s2t");
+    S2T e;
+    e.src = src_[src_name];
+    e.trg = trg_[trg_name].slot;
+    e.kid = id;
+    e.ctx = ker_s2t.GetCtxPtr();
+    push_s2t(e);
+    drop_s2t(e.src, e.trg);
+    if (e.ctx) s2t_ctx_.push_back(e);  // re-read at every EvalDirect
   }
 
   void DeleteSrc(const std::string& name) {
     SCTL_CUDA_ASSERT(src_.find(name) != src_.end());
-    for (auto& t : trg_) sctl_cuda_direct_set_kernel_s2t(h_, src_[name], t.second.slot, -1, nullptr, 0);
-    sctl_cuda_direct_set_src_coord(h_, src_[name], 0, nullptr, nullptr, 0);
+    const int slot = src_[name];
+    for (auto& t : trg_) {
+      sctl_cuda_direct_set_kernel_s2t(h_, slot, t.second.slot, -1, nullptr, 0);
+      drop_s2t(slot, t.second.slot);
+    }
+    sctl_cuda_direct_set_src_coord(h_, slot, 0, nullptr, nullptr, 0);
+    sctl_cuda_direct_set_src_density(h_, slot, 0, nullptr);
     src_.erase(name);
+    free_src_.push_back(slot);  // slot numbers are bounded by the C ABI: reuse them
   }
   void DeleteTrg(const std::string& name) {
     SCTL_CUDA_ASSERT(trg_.find(name) != trg_.end());
-    for (auto& s : src_) sctl_cuda_direct_set_kernel_s2t(h_, s.second, trg_[name].slot, -1, nullptr, 0);
-    sctl_cuda_direct_set_trg_coord(h_, trg_[name].slot, 0, nullptr);
+    const int slot = trg_[name].slot;
+    for (auto& s : src_) {
+      sctl_cuda_direct_set_kernel_s2t(h_, s.second, slot, -1, nullptr, 0);
+      drop_s2t(s.second, slot);
+    }
+    sctl_cuda_direct_set_trg_coord(h_, slot, 0, nullptr);
     trg_.erase(name);
+    free_trg_.push_back(slot);
   }
 
   template <class Vec> void SetSrcCoord(const std::string& name, const Vec& src_coord, const Vec& src_normal) {
@@ -114,6 +142,8 @@ template <class Real, Integer DIM = 3> class ParticleDirect {
     SCTL_CUDA_ASSERT(it != trg_.end());  // "Target name does not exist." (:555)
     const Long n = it->second.Nt * it->second.dim;
     if (U.Dim() != n) U.ReInit(n);
+    for (const S2T& e : s2t_ctx_)  // the reference dereferences ctx_ptr at every Eval: pick up a changed wavenumber
+      if (e.trg == it->second.slot) push_s2t(e);
     if (sctl_cuda_direct_eval(h_, it->second.slot, (int)(digits_ >= 16 ? -1 : digits_), n ? &U[0] : nullptr, n)) detail::die("sctl_cuda_direct_eval");
   }
   template <class Vec> void Eval(Vec& U, const std::string& trg_name) const { EvalDirect(U, trg_name); }
@@ -124,9 +154,29 @@ template <class Real, Integer DIM = 3> class ParticleDirect {
     Integer dim;
     Long Nt;
   };
+  struct S2T {
+    int src, trg, kid;
+    const void* ctx;
+  };
+  void push_s2t(const S2T& e) const {
+    if (sctl_cuda_direct_set_kernel_s2t(h_, e.src, e.trg, e.kid, e.ctx, e.ctx ? (int64_t)sizeof(Real) : 0)) detail::die("sctl_cuda_direct_set_kernel_s2t");
+  }
+  void drop_s2t(int src, int trg) {
+    for (size_t i = 0; i < s2t_ctx_.size();)
+      if (s2t_ctx_[i].src == src && s2t_ctx_[i].trg == trg) s2t_ctx_.erase(s2t_ctx_.begin() + i);
+      else i++;
+  }
+  static int take_slot(std::vector<int>& free_list, int& next) {
+    if (free_list.empty()) return next++;
+    const int s = free_list.back();
+    free_list.pop_back();
+    return s;
+  }
   sctl_cuda_direct_t h_;
   Integer digits_;
   int next_src_ = 0, next_trg_ = 0;
+  std::vector<int> free_src_, free_trg_;
+  std::vector<S2T> s2t_ctx_;  // interactions whose kernel has a context pointer
   std::map<std::string, int> src_;
   std::map<std::string, Trg> trg_;
 };

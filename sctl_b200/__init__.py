@@ -56,6 +56,8 @@ def load_library():
     L.sctl_cuda_set_option.argtypes = [C.c_char_p, i64]
     L.sctl_cuda_const_geometry.argtypes = [i, i, i64, i64, i, ip, ip, ip, ip, ip, C.POINTER(i64), C.POINTER(i64)]
     L.sctl_cuda_direct_create.argtypes = [i, i, C.POINTER(vp)]
+    L.sctl_cuda_direct_create_on.argtypes = [i, i, ip, C.POINTER(vp)]
+    L.sctl_cuda_direct_devices.argtypes = [vp, ip, ip, i]
     L.sctl_cuda_direct_destroy.argtypes = [vp]
     L.sctl_cuda_direct_set_src_coord.argtypes = [vp, i, i64, vp, vp, i]
     L.sctl_cuda_direct_set_src_density.argtypes = [vp, i, i64, vp]
@@ -364,14 +366,30 @@ class ParticleDirect:
     """Device-resident direct evaluator: the ``ParticleFMM::EvalDirect`` analogue (fmm-wrapper.hpp:35-200,
     fmm-wrapper.txx:551-623) over ``sctl_cuda_direct_*``.  Same method names and argument meaning as ``ParticleFMM``
     for the subset EvalDirect uses; coordinates are uploaded once and stay in HBM, an apply ships only the density in
-    and the potential out.  ``n_gpus > 1`` shards the targets over GPUs 0..n_gpus-1 (results agree to rounding for any n_gpus)."""
+    and the potential out.  ``n_gpus > 1`` shards the targets over GPUs 0..n_gpus-1 (results agree to rounding for any
+    n_gpus); ``n_gpus == 1`` uses the device that is current on the creating thread (one rank per GPU: the rank's own
+    GPU); ``devices=[...]`` names the CUDA device ordinals explicitly.  A kernel's context (the Helmholtz wavenumber
+    set with ``SetCtxPtr``) is read again at every ``EvalDirect``, as the reference dereferences ``ctx_ptr`` at every
+    Eval."""
 
-    def __init__(self, dtype=np.float64, n_gpus=1):
+    def __init__(self, dtype=np.float64, n_gpus=1, devices=None):
         self._dtype = np.dtype(dtype).type
         self._h = C.c_void_p()
         self._src, self._trg = {}, {}
+        self._s2t = {}  # (src slot, trg slot) -> kernel object, for kernels with a context
         self._digits = 10  # ParticleFMM's default accuracy (fmm-wrapper.txx:205)
-        _check(load_library().sctl_cuda_direct_create(np.dtype(dtype).itemsize, int(n_gpus), C.byref(self._h)))
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+            _check(load_library().sctl_cuda_direct_create_on(np.dtype(dtype).itemsize, len(devices), devs, C.byref(self._h)))
+        else:
+            _check(load_library().sctl_cuda_direct_create(np.dtype(dtype).itemsize, int(n_gpus), C.byref(self._h)))
+
+    def devices(self):
+        """CUDA device ordinals of the session's GPUs."""
+        n = C.c_int(0)
+        devs = (C.c_int * 16)()
+        _check(load_library().sctl_cuda_direct_devices(self._h, C.byref(n), devs, 16))
+        return [int(devs[i]) for i in range(n.value)]
 
     def close(self):
         if self._h:
@@ -405,14 +423,21 @@ class ParticleDirect:
 
     def SetKernelS2T(self, src_name, trg_name, ker_s2t):
         k = ker_s2t if isinstance(ker_s2t, GenericKernel) else GenericKernel(ker_s2t)
+        st = (self._slot(self._src, src_name, "Source"), self._slot(self._trg, trg_name, "Target"))
+        self._push_s2t(st, k)
+        self._s2t.pop(st, None)
+        if k.GetCtxPtr() is not None:
+            self._s2t[st] = k
+
+    def _push_s2t(self, st, k):
         ctx, nb = k._ctx_arg(self._dtype)
-        _check(load_library().sctl_cuda_direct_set_kernel_s2t(self._h, self._slot(self._src, src_name, "Source"), self._slot(self._trg, trg_name, "Target"),
-                                                              k.kernel_id, _np_ptr(ctx), nb))
+        _check(load_library().sctl_cuda_direct_set_kernel_s2t(self._h, st[0], st[1], k.kernel_id, _np_ptr(ctx), nb))
 
     def DeleteSrc(self, name):
         s = self._slot(self._src, name, "Source")
         for t in self._trg.values():
             _check(load_library().sctl_cuda_direct_set_kernel_s2t(self._h, s, t, -1, None, 0))
+            self._s2t.pop((s, t), None)
         _check(load_library().sctl_cuda_direct_set_src_coord(self._h, s, 0, None, None, 0))
         del self._src[name]
 
@@ -420,6 +445,7 @@ class ParticleDirect:
         t = self._slot(self._trg, name, "Target")
         for s in self._src.values():
             _check(load_library().sctl_cuda_direct_set_kernel_s2t(self._h, s, t, -1, None, 0))
+            self._s2t.pop((s, t), None)
         _check(load_library().sctl_cuda_direct_set_trg_coord(self._h, t, 0, None))
         del self._trg[name]
 
@@ -456,6 +482,9 @@ class ParticleDirect:
         n = self._nt[trg_name] * int(trg_dim)
         if U is None or not isinstance(U, np.ndarray) or U.size != n or U.dtype != self._dtype or not U.flags.c_contiguous:
             U = np.zeros(n, dtype=self._dtype)
+        for st, k in self._s2t.items():  # a context changed since SetKernelS2T takes effect, as in the reference
+            if st[1] == t:
+                self._push_s2t(st, k)
         _check(load_library().sctl_cuda_direct_eval(self._h, t, self._digits, _np_ptr(U.reshape(-1)), n))
         return U
 

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
 #include <memory>
 #include <mutex>
@@ -53,18 +54,38 @@ int fail(const char* fmt, ...) {
 // ---------------------------------------------------------------------------------------------
 constexpr int MAX_DEV = 16;
 
+// Per (host thread, device) resources.  A thread that ends hands them back to a process-wide pool instead of leaking
+// them (applications that create and destroy many threads would otherwise leak 1 MB of pinned memory per thread); the
+// next new thread takes them over, and sctl_cuda_finalize() releases whatever sits in the pool.
+struct DevRes {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {};
+  // small-call arena: one pinned host buffer and one device buffer, see eval_host_small()
+  char* arena_h = nullptr;
+  char* arena_d = nullptr;
+  bool empty() const { return !stream && !arena_h; }
+};
+struct ResPool {
+  std::mutex mu;
+  std::vector<DevRes> idle[MAX_DEV];
+};
+// never destroyed: thread_local destructors (which return resources) may run after static destructors would have
+ResPool& res_pool() {
+  static ResPool* p = new ResPool();
+  return *p;
+}
+
 struct ThreadState {
-  cudaStream_t stream[MAX_DEV] = {};
-  cudaEvent_t ev[MAX_DEV][4] = {};
-  // small-call arena: one pinned host buffer and one device buffer per (thread, device), see eval_host_small()
-  char* arena_h[MAX_DEV] = {};
-  char* arena_d[MAX_DEV] = {};
+  DevRes res[MAX_DEV];
   double h2d_ms = 0, kernel_ms = 0, d2h_ms = 0;
   int grid_x = 0, grid_y = 0, threads = 0, smem = 0, ctas_per_sm = 0, n_launches = 0;
   double wave_eff = 0;
   ~ThreadState() {
-    // streams/events are left to the driver at process exit (destroying them after the primary
-    // context is gone is an error); threads that end early leak a few handles at most.
+    // no CUDA calls here (the primary context may already be gone at process exit): just park the handles
+    ResPool& pool = res_pool();
+    std::lock_guard<std::mutex> lk(pool.mu);
+    for (int d = 0; d < MAX_DEV; d++)
+      if (!res[d].empty()) pool.idle[d].push_back(res[d]);
   }
 };
 thread_local ThreadState tl;
@@ -158,12 +179,22 @@ int ensure_device_info(int dev) {
 
 int ensure_device(int dev) {
   if (ensure_device_info(dev)) return 1;
-  if (!tl.stream[dev]) {
+  DevRes& r = tl.res[dev];
+  if (!r.stream) {
+    {  // a finished thread's resources, if any
+      ResPool& pool = res_pool();
+      std::lock_guard<std::mutex> lk(pool.mu);
+      if (!pool.idle[dev].empty()) {
+        r = pool.idle[dev].back();
+        pool.idle[dev].pop_back();
+      }
+    }
+    if (r.stream) return 0;
     int cur;
     CU_TRY(cudaGetDevice(&cur));
     CU_TRY(cudaSetDevice(dev));
-    CU_TRY(cudaStreamCreateWithFlags(&tl.stream[dev], cudaStreamNonBlocking));
-    for (int i = 0; i < 4; i++) CU_TRY(cudaEventCreate(&tl.ev[dev][i]));
+    CU_TRY(cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++) CU_TRY(cudaEventCreate(&r.ev[i]));
     CU_TRY(cudaSetDevice(cur));
   }
   return 0;
@@ -216,6 +247,20 @@ template <> struct Tune<float> {
   static constexpr int CONST_T = 4, CONST_NT = 128, CONST_U = 2, CONST_MINB = 4;
 };
 
+struct DevBuf {
+  void* p = nullptr;
+  cudaStream_t st = nullptr;
+  int alloc(size_t bytes, cudaStream_t s) {
+    st = s;
+    if (bytes == 0) return 0;
+    CU_TRY(cudaMallocAsync(&p, bytes, s));
+    return 0;
+  }
+  ~DevBuf() {
+    if (p) cudaFreeAsync(p, st);
+  }
+};
+
 struct OccCache {
   std::mutex mu;
   int ctas[MAX_DEV] = {};
@@ -256,7 +301,11 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
   a.ctx0 = ctx0;
   constexpr int K1 = KerTraits<KID>::K1;
   int n_launches = 1;
-  if (plan.n_split > 1) CU_TRY(cudaMallocAsync((void**)&a.partial, sizeof(Real) * (size_t)plan.n_split * Nt * K1, stream));
+  DevBuf partial;  // stream-ordered free on every exit path
+  if (plan.n_split > 1) {
+    if (partial.alloc(sizeof(Real) * (size_t)plan.n_split * Nt * K1, stream)) return 1;
+    a.partial = (Real*)partial.p;
+  }
   dim3 grid((unsigned)plan.n_tblocks, (unsigned)plan.n_split);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(a);
   CU_TRY(cudaGetLastError());
@@ -265,7 +314,6 @@ int launch_eval_cfg(int dev, int64_t Ns, int64_t Nt, const Real* pack, const Rea
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
     reduce_partials_kernel<Real><<<blocks, 256, 0, stream>>>(n, plan.n_split, a.partial, a.scale, v_trg);
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaFreeAsync(a.partial, stream));
     n_launches = 2;
   }
   tl.grid_x = (int)grid.x;
@@ -334,14 +382,37 @@ int launch_eval_const(int dev, const ConstGeom& cg, bool use_bits, int64_t Ns, i
   } else {
     CU_TRY(cudaStreamWaitEvent(stream, di.const_done, 0));  // the previous user of the constant bank, on any stream
   }
+  // Whatever happens below, the shared per-device state must be left consistent for the next caller (on any stream):
+  // the bank streams joined back into `stream`, the scratch buffer freed behind everything that uses it, and const_done
+  // recorded behind the last reader of c_src_pack / c_eval_must_mask.  The guard does that on every exit path.
+  struct Join {
+    DeviceInfo& di;
+    cudaStream_t stream;
+    int banks;
+    bool forked = false, joined = false;
+    void* alt = nullptr;
+    void join() {
+      if (forked && !joined)
+        for (int b = 1; b < banks; b++)
+          if (cudaEventRecord(di.bank_done[b], di.bank_stream[b]) == cudaSuccess) cudaStreamWaitEvent(stream, di.bank_done[b], 0);
+      joined = true;
+    }
+    ~Join() {
+      join();
+      if (alt) cudaFreeAsync(alt, stream);
+      cudaEventRecord(di.const_done, stream);
+    }
+  } guard{di, stream, banks};
   if (flags) CU_TRY(cudaMemcpyToSymbolAsync(c_eval_must_mask, flags, 2 * sizeof(int), 0, cudaMemcpyDeviceToDevice, stream));
   // banks 1.. accumulate into their own zeroed buffers (launches of different banks overlap and must not race on v_trg)
   Real* alt = nullptr;
   const size_t nv = (size_t)Nt * K1;
   if (banks > 1) {
     CU_TRY(cudaMallocAsync((void**)&alt, sizeof(Real) * nv * (banks - 1), stream));
+    guard.alt = alt;
     CU_TRY(cudaMemsetAsync(alt, 0, sizeof(Real) * nv * (banks - 1), stream));
     CU_TRY(cudaEventRecord(di.const_fork, stream));
+    guard.forked = true;
     for (int b = 1; b < banks; b++) CU_TRY(cudaStreamWaitEvent(di.bank_stream[b], di.const_fork, 0));
   }
   int launches = 0;
@@ -365,17 +436,12 @@ int launch_eval_const(int dev, const ConstGeom& cg, bool use_bits, int64_t Ns, i
     launches++;
   }
   if (banks > 1) {
-    for (int b = 1; b < banks; b++) {
-      CU_TRY(cudaEventRecord(di.bank_done[b], di.bank_stream[b]));
-      CU_TRY(cudaStreamWaitEvent(stream, di.bank_done[b], 0));
-    }
+    guard.join();
     const int blocks = (int)std::min<int64_t>(((int64_t)nv + 255) / 256, 4096);
     reduce_partials_kernel<Real><<<blocks, 256, 0, stream>>>((int64_t)nv, banks - 1, alt, (Real)1, v_trg);  // bank order: deterministic
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaFreeAsync(alt, stream));
     launches++;
   }
-  CU_TRY(cudaEventRecord(di.const_done, stream));
   tl.grid_x = (int)n_tb;
   tl.grid_y = cl;
   tl.threads = NT;
@@ -401,8 +467,9 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
   const bool use_bits = use_const && cg.row_words && probe && g.opt.probe_per_block != 0;
   // packed sources: contiguous records, or chunk segments (records + coincidence bits) for the constant-bank path
   const size_t pack_bytes = use_const ? (size_t)cg.n_chunks * cg.seg_bytes : sizeof(Real) * (size_t)Ns * REC;
-  Real* pack = nullptr;
-  CU_TRY(cudaMallocAsync((void**)&pack, pack_bytes, stream));
+  DevBuf pack_buf, table_buf;  // freed (stream-ordered) on every exit path, after everything enqueued below
+  if (pack_buf.alloc(pack_bytes, stream)) return 1;
+  Real* pack = (Real*)pack_buf.p;
   if (use_bits) CU_TRY(cudaMemsetAsync(pack, 0, pack_bytes, stream));  // the bit rows start clear
   {
     const int blocks = (int)std::min<int64_t>((Ns + 255) / 256, 8192);
@@ -419,7 +486,8 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
     const bool bits = use_bits;
     // [slots keys | 2 flags (one 64-bit word) | pad] [cmin | cmax]
     const size_t key_bytes = (slots + 2) * sizeof(unsigned long long);
-    CU_TRY(cudaMallocAsync((void**)&table, key_bytes + (bits ? 2 * slots * sizeof(unsigned) : 0), stream));
+    if (table_buf.alloc(key_bytes + (bits ? 2 * slots * sizeof(unsigned) : 0), stream)) return 1;
+    table = (unsigned long long*)table_buf.p;
     CU_TRY(cudaMemsetAsync(table, 0, key_bytes + (bits ? 2 * slots * sizeof(unsigned) : 0), stream));
     flags = reinterpret_cast<int*>(table + slots);
     CoincidenceBits cb = {};
@@ -446,14 +514,9 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
     rc = launch_eval_cfg<Real, KID, Tn::FEW_T, Tn::FEW_NW, Tn::FEW_NW, RSQ, Tn::FEW_TILE, Tn::FEW_STAGES, Tn::FEW_MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, Tn::FEW_TILE, 1024);
   else
     rc = launch_eval_cfg<Real, KID, Tn::T, Tn::NW, 1, RSQ, Tn::TILE, Tn::STAGES, Tn::MINB>(dev, Ns, Nt, pack, r_trg, v_trg, flags, ctx0, stream, (int)g.opt.ring_min_tiles * Tn::TILE, (int)g.opt.ring_max_split);
-  if (table) cudaFreeAsync(table, stream);
   tl.n_launches += n_probe_launches;
-  if (rc) {
-    cudaFreeAsync(pack, stream);
-    return rc;
-  }
+  if (rc) return rc;
   tl.n_launches += 1;  // the pack kernel
-  CU_TRY(cudaFreeAsync(pack, stream));
   return 0;
 }
 
@@ -608,7 +671,7 @@ template <class Real> int fma_peak_t(double ms, double* tflops) {
   int dev;
   CU_TRY(cudaGetDevice(&dev));
   if (ensure_device(dev)) return 1;
-  cudaStream_t st = tl.stream[dev];
+  cudaStream_t st = tl.res[dev].stream;
   Real* out;
   CU_TRY(cudaMallocAsync((void**)&out, sizeof(Real), st));
   const int blocks = g.dev[dev].sms * 8, threads = 256;
@@ -616,11 +679,11 @@ template <class Real> int fma_peak_t(double ms, double* tflops) {
   float t = 0;
   double best = 0;
   for (int rep = 0; rep < 6; rep++) {
-    CU_TRY(cudaEventRecord(tl.ev[dev][0], st));
+    CU_TRY(cudaEventRecord(tl.res[dev].ev[0], st));
     fma_peak_kernel<Real><<<blocks, threads, 0, st>>>(iters, out, (Real)0.5);
-    CU_TRY(cudaEventRecord(tl.ev[dev][1], st));
-    CU_TRY(cudaEventSynchronize(tl.ev[dev][1]));
-    CU_TRY(cudaEventElapsedTime(&t, tl.ev[dev][0], tl.ev[dev][1]));
+    CU_TRY(cudaEventRecord(tl.res[dev].ev[1], st));
+    CU_TRY(cudaEventSynchronize(tl.res[dev].ev[1]));
+    CU_TRY(cudaEventElapsedTime(&t, tl.res[dev].ev[0], tl.res[dev].ev[1]));
     const double flop = 2.0 * 64.0 * iters * (double)blocks * threads;
     if (rep > 0) best = std::max(best, flop / (t * 1e-3) * 1e-12);
     if (t < ms && rep < 4) iters = (int)std::min<double>(2.0e6, iters * std::max(1.5, ms / std::max(t, 0.01f)));
@@ -645,20 +708,6 @@ int current_device_ready(int* dev) {
   return ensure_device(*dev);
 }
 
-struct DevBuf {
-  void* p = nullptr;
-  cudaStream_t st = nullptr;
-  int alloc(size_t bytes, cudaStream_t s) {
-    st = s;
-    if (bytes == 0) return 0;
-    CU_TRY(cudaMallocAsync(&p, bytes, s));
-    return 0;
-  }
-  ~DevBuf() {
-    if (p) cudaFreeAsync(p, st);
-  }
-};
-
 // Small calls (all arrays together below SMALL_ARENA bytes) are latency-bound: five pageable uploads, five pool
 // allocations and a pageable download cost more than the kernel.  They go through a per-thread arena instead: the inputs
 // are gathered into ONE pinned buffer, uploaded with one copy into a persistent device buffer, and the result comes back
@@ -668,9 +717,9 @@ constexpr size_t SMALL_ARENA = 1 << 20;
 inline size_t arena_align(size_t n) { return (n + 255) & ~(size_t)255; }
 
 int ensure_arena(int dev) {
-  if (tl.arena_h[dev]) return 0;
-  CU_TRY(cudaHostAlloc((void**)&tl.arena_h[dev], SMALL_ARENA, cudaHostAllocDefault));
-  CU_TRY(cudaMalloc((void**)&tl.arena_d[dev], SMALL_ARENA));
+  if (tl.res[dev].arena_h) return 0;
+  CU_TRY(cudaHostAlloc((void**)&tl.res[dev].arena_h, SMALL_ARENA, cudaHostAllocDefault));
+  CU_TRY(cudaMalloc((void**)&tl.res[dev].arena_d, SMALL_ARENA));
   return 0;
 }
 
@@ -683,26 +732,26 @@ int eval_host_small(int dev, int kid, int real_bytes, int digits, int64_t Ns, in
   const size_t total = o_rt + arena_align(b_rt);
   CU_TRY(cudaSetDevice(dev));
   if (ensure_device(dev) || ensure_arena(dev)) return 1;
-  cudaStream_t st = tl.stream[dev];
-  char *h = tl.arena_h[dev], *d = tl.arena_d[dev];
+  cudaStream_t st = tl.res[dev].stream;
+  char *h = tl.res[dev].arena_h, *d = tl.res[dev].arena_d;
   memcpy(h + o_vt, v_trg, b_vt);
   memcpy(h + o_rs, r_src, b_rs);
   memcpy(h + o_vs, v_src, b_vs);
   if (b_ns) memcpy(h + o_ns, n_src, b_ns);
   memcpy(h + o_rt, r_trg, b_rt);
-  CU_TRY(cudaEventRecord(tl.ev[dev][0], st));
+  CU_TRY(cudaEventRecord(tl.res[dev].ev[0], st));
   CU_TRY(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaEventRecord(tl.ev[dev][1], st));
+  CU_TRY(cudaEventRecord(tl.res[dev].ev[1], st));
   if (eval_device_any(dev, kid, real_bytes, digits, Ns, Nt, d + o_rs, b_ns ? d + o_ns : nullptr, d + o_vs, d + o_rt, d + o_vt, ctx0, st)) return 1;
-  CU_TRY(cudaEventRecord(tl.ev[dev][2], st));
+  CU_TRY(cudaEventRecord(tl.res[dev].ev[2], st));
   CU_TRY(cudaMemcpyAsync(h + o_vt, d + o_vt, b_vt, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaEventRecord(tl.ev[dev][3], st));
+  CU_TRY(cudaEventRecord(tl.res[dev].ev[3], st));
   CU_TRY(cudaStreamSynchronize(st));
   memcpy(v_trg, h + o_vt, b_vt);
   float a = 0, b = 0, c = 0;
-  CU_TRY(cudaEventElapsedTime(&a, tl.ev[dev][0], tl.ev[dev][1]));
-  CU_TRY(cudaEventElapsedTime(&b, tl.ev[dev][1], tl.ev[dev][2]));
-  CU_TRY(cudaEventElapsedTime(&c, tl.ev[dev][2], tl.ev[dev][3]));
+  CU_TRY(cudaEventElapsedTime(&a, tl.res[dev].ev[0], tl.res[dev].ev[1]));
+  CU_TRY(cudaEventElapsedTime(&b, tl.res[dev].ev[1], tl.res[dev].ev[2]));
+  CU_TRY(cudaEventElapsedTime(&c, tl.res[dev].ev[2], tl.res[dev].ev[3]));
   tl.h2d_ms = a;
   tl.kernel_ms = b;
   tl.d2h_ms = c;
@@ -717,27 +766,27 @@ int eval_host_one(int dev, int kid, int real_bytes, int digits, int64_t Ns, int6
   const int64_t nt = t1 - t0;
   CU_TRY(cudaSetDevice(dev));
   if (ensure_device(dev)) return 1;
-  cudaStream_t st = tl.stream[dev];
+  cudaStream_t st = tl.res[dev].stream;
   DevBuf d_rs, d_ns, d_vs, d_rt, d_vt;
   if (d_rs.alloc(rb * Ns * 3, st) || d_vs.alloc(rb * Ns * ki.k0, st) || d_rt.alloc(rb * nt * 3, st) || d_vt.alloc(rb * nt * ki.k1, st)) return 1;
   if (ki.nd && d_ns.alloc(rb * Ns * ki.nd, st)) return 1;
-  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][0], st));
+  if (timing) CU_TRY(cudaEventRecord(tl.res[dev].ev[0], st));
   CU_TRY(cudaMemcpyAsync(d_rs.p, r_src, rb * Ns * 3, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(d_vs.p, v_src, rb * Ns * ki.k0, cudaMemcpyHostToDevice, st));
   if (ki.nd) CU_TRY(cudaMemcpyAsync(d_ns.p, n_src, rb * Ns * ki.nd, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg + rb * t0 * 3, rb * nt * 3, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(d_vt.p, v_trg + rb * t0 * ki.k1, rb * nt * ki.k1, cudaMemcpyHostToDevice, st));
-  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][1], st));
+  if (timing) CU_TRY(cudaEventRecord(tl.res[dev].ev[1], st));
   if (eval_device_any(dev, kid, real_bytes, digits, Ns, nt, d_rs.p, d_ns.p, d_vs.p, d_rt.p, d_vt.p, ctx0, st)) return 1;
-  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][2], st));
+  if (timing) CU_TRY(cudaEventRecord(tl.res[dev].ev[2], st));
   CU_TRY(cudaMemcpyAsync(v_trg + rb * t0 * ki.k1, d_vt.p, rb * nt * ki.k1, cudaMemcpyDeviceToHost, st));
-  if (timing) CU_TRY(cudaEventRecord(tl.ev[dev][3], st));
+  if (timing) CU_TRY(cudaEventRecord(tl.res[dev].ev[3], st));
   CU_TRY(cudaStreamSynchronize(st));
   if (timing) {
     float a = 0, b = 0, c = 0;
-    CU_TRY(cudaEventElapsedTime(&a, tl.ev[dev][0], tl.ev[dev][1]));
-    CU_TRY(cudaEventElapsedTime(&b, tl.ev[dev][1], tl.ev[dev][2]));
-    CU_TRY(cudaEventElapsedTime(&c, tl.ev[dev][2], tl.ev[dev][3]));
+    CU_TRY(cudaEventElapsedTime(&a, tl.res[dev].ev[0], tl.res[dev].ev[1]));
+    CU_TRY(cudaEventElapsedTime(&b, tl.res[dev].ev[1], tl.res[dev].ev[2]));
+    CU_TRY(cudaEventElapsedTime(&c, tl.res[dev].ev[2], tl.res[dev].ev[3]));
     tl.h2d_ms = a;
     tl.kernel_ms = b;
     tl.d2h_ms = c;
@@ -755,16 +804,35 @@ struct ShardResult {
   double h2d = 0, ker = 0, d2h = 0;
 };
 
+// All P shard threads meet here once, after their fallible local work (device selection, allocations, uploads) and
+// before the first collective: if any of them failed, none enters the NCCL group -- otherwise the survivors would
+// enqueue broadcasts that can never complete and block in cudaStreamSynchronize for ever.
+struct ShardGate {
+  explicit ShardGate(int P_) : P(P_) {}
+  std::mutex mu;
+  std::condition_variable cv;
+  int P, arrived = 0;
+  bool failed = false;
+  bool arrive(bool ok) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (!ok) failed = true;
+    if (++arrived == P) cv.notify_all();
+    else cv.wait(lk, [&] { return arrived == P; });
+    return !failed;
+  }
+};
+
 void eval_host_shard(int p, int P, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const char* r_src, const char* n_src, const char* v_src,
-                     const char* r_trg, char* v_trg, double ctx0, ShardResult* res) {
-  auto body = [&]() -> int {
-    const KernelInfo ki = kernel_info(kid);
-    const size_t rb = (size_t)real_bytes;
-    const int64_t t0 = Nt * p / P, t1 = Nt * (p + 1) / P, nt = t1 - t0;
+                     const char* r_trg, char* v_trg, double ctx0, ShardGate* gate, ShardResult* res) {
+  const KernelInfo ki = kernel_info(kid);
+  const size_t rb = (size_t)real_bytes;
+  const int64_t t0 = Nt * p / P, t1 = Nt * (p + 1) / P, nt = t1 - t0;
+  cudaStream_t st = g.mstream[p];
+  cudaEvent_t* ev = g.mev[p];
+  DevBuf d_rs, d_ns, d_vs, d_rt, d_vt;
+  // everything that can fail without the other shards noticing
+  auto before_collective = [&]() -> int {
     CU_TRY(cudaSetDevice(p));
-    cudaStream_t st = g.mstream[p];
-    cudaEvent_t* ev = g.mev[p];
-    DevBuf d_rs, d_ns, d_vs, d_rt, d_vt;
     if (d_rs.alloc(rb * Ns * 3, st) || d_vs.alloc(rb * Ns * ki.k0, st) || d_rt.alloc(rb * std::max<int64_t>(nt, 1) * 3, st) ||
         d_vt.alloc(rb * std::max<int64_t>(nt, 1) * ki.k1, st))
       return 1;
@@ -778,6 +846,9 @@ void eval_host_shard(int p, int P, int kid, int real_bytes, int digits, int64_t 
       CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg + rb * t0 * 3, rb * nt * 3, cudaMemcpyHostToDevice, st));
       CU_TRY(cudaMemcpyAsync(d_vt.p, v_trg + rb * t0 * ki.k1, rb * nt * ki.k1, cudaMemcpyHostToDevice, st));
     }
+    return 0;
+  };
+  auto collective_and_after = [&]() -> int {
     // replicate the source slices: root q broadcasts its slice into the same offsets on every GPU
     const ncclDataType_t dt = real_bytes == 8 ? ncclFloat64 : ncclFloat32;
     ncclResult_t nr = g.nccl.GroupStart();
@@ -812,7 +883,17 @@ void eval_host_shard(int p, int P, int kid, int real_bytes, int digits, int64_t 
     res->d2h = c;
     return 0;
   };
-  res->rc = body();
+  res->rc = before_collective();
+  if (res->rc) res->err = tl_err;
+  if (!gate->arrive(res->rc == 0)) {
+    if (!res->rc) {
+      res->rc = 1;
+      res->err = "cancelled: another GPU's shard failed before the broadcast";
+    }
+    cudaStreamSynchronize(st);  // the uploads read the caller's arrays
+    return;
+  }
+  res->rc = collective_and_after();
   if (res->rc) res->err = tl_err;
 }
 
@@ -838,7 +919,47 @@ int sctl_cuda_num_gpus(void) {
   return g.n_gpus;
 }
 
+namespace {
+// caller holds g.multi_mu
+int finalize_locked() {
+  std::lock_guard<std::mutex> lk(g.mu);
+  if (g.have_comms) {
+    for (int i = 0; i < g.n_gpus; i++)
+      if (g.comms[i]) g.nccl.CommDestroy(g.comms[i]);
+    memset(g.comms, 0, sizeof(g.comms));
+    g.have_comms = false;
+  }
+  g.n_gpus = 0;
+  // resources parked by threads that have ended
+  ResPool& pool = res_pool();
+  std::lock_guard<std::mutex> plk(pool.mu);
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) cur = -1;
+  for (int d = 0; d < MAX_DEV; d++) {
+    if (pool.idle[d].empty()) continue;
+    if (cudaSetDevice(d) == cudaSuccess)
+      for (DevRes& r : pool.idle[d]) {
+        if (r.stream) {
+          cudaStreamSynchronize(r.stream);
+          cudaStreamDestroy(r.stream);
+        }
+        for (cudaEvent_t e : r.ev)
+          if (e) cudaEventDestroy(e);
+        if (r.arena_h) cudaFreeHost(r.arena_h);
+        if (r.arena_d) cudaFree(r.arena_d);
+      }
+    pool.idle[d].clear();
+  }
+  if (cur >= 0) cudaSetDevice(cur);
+  cudaGetLastError();
+  return 0;
+}
+}  // namespace
+
 int sctl_cuda_init(int n_gpus) {
+  // multi_mu first, then g.mu (the order of sctl_cuda_eval's sharded path): a sharded Eval in flight keeps its
+  // communicators until it has finished
+  std::lock_guard<std::mutex> mlk(g.multi_mu);
   const int vis = visible_devices();
   if (vis < 1) return fail("no CUDA device available (libsctl_cuda has no CPU fallback)");
   if (n_gpus < 0 || n_gpus > vis) return fail("requested %d GPUs, %d visible", n_gpus, vis);
@@ -848,7 +969,7 @@ int sctl_cuda_init(int n_gpus) {
     std::lock_guard<std::mutex> lk(g.mu);
     if (g.have_comms && g.n_gpus == n_gpus) return 0;
   }
-  if (sctl_cuda_finalize()) return 1;
+  if (finalize_locked()) return 1;
   if (n_gpus > 1) {
     std::lock_guard<std::mutex> lk(g.mu);
     if (!g.nccl.handle) {
@@ -888,15 +1009,8 @@ int sctl_cuda_init(int n_gpus) {
 }
 
 int sctl_cuda_finalize(void) {
-  std::lock_guard<std::mutex> lk(g.mu);
-  if (g.have_comms) {
-    for (int i = 0; i < g.n_gpus; i++)
-      if (g.comms[i]) g.nccl.CommDestroy(g.comms[i]);
-    memset(g.comms, 0, sizeof(g.comms));
-    g.have_comms = false;
-  }
-  g.n_gpus = 0;
-  return 0;
+  std::lock_guard<std::mutex> mlk(g.multi_mu);
+  return finalize_locked();
 }
 
 int sctl_cuda_kernel_info(int kernel_id, int* k0, int* k1, int* nd, int* flops, int* f_alg, double* scale, const char** name) {
@@ -952,13 +1066,24 @@ int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_
     comms = g.have_comms;
   }
   if (P > 1 && comms && (double)Ns * (double)Nt >= MULTI_GPU_MIN_PAIRS && Nt >= P) {
-    std::lock_guard<std::mutex> mlk(g.multi_mu);
+    std::unique_lock<std::mutex> mlk(g.multi_mu);
+    {  // init / finalize also take multi_mu: what was read above may be stale by now
+      std::lock_guard<std::mutex> lk(g.mu);
+      if (g.n_gpus != P || !g.have_comms) P = 0;
+    }
+    if (P == 0) {
+      mlk.unlock();
+      return sctl_cuda_eval(kernel_id, real_bytes, digits, Ns, Nt, r_src, n_src, v_src, r_trg, v_trg, ctx, ctx_bytes);
+    }
     std::vector<ShardResult> res(P);
     std::vector<std::thread> th;
+    ShardGate gate(P);
     for (int p = 0; p < P; p++)
       th.emplace_back(eval_host_shard, p, P, kernel_id, real_bytes, digits, Ns, Nt, (const char*)r_src, (const char*)n_src, (const char*)v_src,
-                      (const char*)r_trg, (char*)v_trg, ctx0, &res[p]);
+                      (const char*)r_trg, (char*)v_trg, ctx0, &gate, &res[p]);
     for (auto& t : th) t.join();
+    for (int p = 0; p < P; p++)  // report the shard that failed first-hand, not one that was merely cancelled
+      if (res[p].rc && res[p].err.compare(0, 10, "cancelled:") != 0) return fail("GPU %d: %s", p, res[p].err.c_str());
     for (int p = 0; p < P; p++) {
       if (res[p].rc) return fail("GPU %d: %s", p, res[p].err.c_str());
       tl.h2d_ms = std::max(tl.h2d_ms, res[p].h2d);
@@ -991,13 +1116,13 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
   const size_t rb = (size_t)real_bytes;
   const int64_t rows = Ns * ki.k0, cols = Nt * ki.k1;
   if (ldM < cols) return fail("ldM (%lld) smaller than Nt*K1 (%lld)", (long long)ldM, (long long)cols);
-  cudaStream_t st = tl.stream[dev];
+  cudaStream_t st = tl.res[dev].stream;
   {  // small-call arena (see eval_host_small): one pinned upload, one pinned download, no pool allocations
     const size_t b_rs = rb * Ns * 3, b_ns = ki.nd ? rb * Ns * ki.nd : 0, b_rt = rb * Nt * 3, b_M = rb * rows * cols;
     const size_t o_rs = 0, o_ns = o_rs + arena_align(b_rs), o_rt = o_ns + arena_align(b_ns), o_M = o_rt + arena_align(b_rt);
     if (o_M + arena_align(b_M) <= SMALL_ARENA && g.opt.small_call_arena) {
       if (ensure_arena(dev)) return 1;
-      char *h = tl.arena_h[dev], *d = tl.arena_d[dev];
+      char *h = tl.res[dev].arena_h, *d = tl.res[dev].arena_d;
       memcpy(h + o_rs, r_src, b_rs);
       if (b_ns) memcpy(h + o_ns, n_src, b_ns);
       memcpy(h + o_rt, r_trg, b_rt);

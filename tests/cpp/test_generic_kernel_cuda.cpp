@@ -192,6 +192,60 @@ template <class R> static void session_layers() {
     R err = 0, mag = 0;
     for (Long i = 0; i < U.Dim(); i++) { err = std::fmax(err, std::fabs(U[i] - V[i])); mag = std::fmax(mag, std::fabs(V[i])); }
     CHECK(err <= tol * mag);
+    // slot numbers are bounded by the C ABI (4096): deleted sources / targets hand theirs back, so long-running callers
+    // that add and delete particle types keep working
+    for (int it = 0; it < 5000; it++) {
+      pd.AddSrc("tmp", sl, sl);
+      pd.AddTrg("tmpT", sl, sl);
+      if (it == 4999) {
+        pd.SetKernelS2T("tmp", "tmpT", sl);
+        pd.SetSrcCoord("tmp", Xs);
+        pd.SetSrcDensity("tmp", F);
+        pd.SetTrgCoord("tmpT", Xt);
+        Vector<R> U2, V2;
+        pd.Eval(U2, "tmpT");
+        sl.template Eval<R, true>(V2, Xt, Xs, none, F);
+        R e2 = 0, m2 = 0;
+        for (Long i = 0; i < U2.Dim(); i++) { e2 = std::fmax(e2, std::fabs(U2[i] - V2[i])); m2 = std::fmax(m2, std::fabs(V2[i])); }
+        CHECK(U2.Dim() == Nt * 3 && e2 <= tol * m2);
+      }
+      pd.DeleteSrc("tmp");
+      pd.DeleteTrg("tmpT");
+    }
+    pd.Eval(U, "T");  // the original interactions are untouched
+    err = 0;
+    for (Long i = 0; i < U.Dim(); i++) err = std::fmax(err, std::fabs(U[i] - V[i]));
+    CHECK(err <= tol * mag);
+  }
+  {  // Helmholtz through the session: the wavenumber is read through the kernel's ctx pointer at every Eval, as the
+     // reference does (the kernel object is copied with its pointer, fmm-wrapper.txx:442-443)
+    R mu = (R)3;
+    sctl_cuda::Helmholtz3D_FxU hk;
+    hk.SetCtxPtr(&mu);
+    Vector<R> F2(Ns * 2), U1, U2, V1, V2, none;
+    for (Long i = 0; i < Ns * 2; i++) F2[i] = F[i];
+    sctl_cuda::ParticleDirect<R> pd;
+    pd.SetAccuracy(-1);
+    pd.AddSrc("H", hk, hk);
+    pd.AddTrg("W", hk, hk);
+    pd.SetKernelS2T("H", "W", hk);
+    pd.SetSrcCoord("H", Xs);
+    pd.SetSrcDensity("H", F2);
+    pd.SetTrgCoord("W", Xt);
+    pd.Eval(U1, "W");
+    hk.template Eval<R, true>(V1, Xt, Xs, none, F2);
+    mu = (R)7.5;  // no new SetKernelS2T
+    pd.Eval(U2, "W");
+    hk.template Eval<R, true>(V2, Xt, Xs, none, F2);
+    R e1 = 0, e2 = 0, d12 = 0, mag = 0;
+    for (Long i = 0; i < U1.Dim(); i++) {
+      e1 = std::fmax(e1, std::fabs(U1[i] - V1[i]));
+      e2 = std::fmax(e2, std::fabs(U2[i] - V2[i]));
+      d12 = std::fmax(d12, std::fabs(V2[i] - V1[i]));
+      mag = std::fmax(mag, std::fabs(V1[i]));
+    }
+    CHECK(e1 <= tol * mag && e2 <= tol * mag);
+    CHECK(d12 > (R)1e-3 * mag);  // the two wavenumbers really give different fields
   }
   {  // two elements (300 and 400 nodes), near targets cut into blocks of 64
     using LV = Vector<Long>;

@@ -76,3 +76,34 @@ def test_particle_direct_two_gpus(sb, cpu_oracle):
     if os.path.exists(exe):
         r = subprocess.run([exe, "2"], capture_output=True, text=True, timeout=600)
         assert r.returncode == 0 and "PASS (0 check(s) failed)" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+def test_particle_direct_follows_the_current_device(sb, cpu_oracle):
+    """One rank per GPU (torchrun, MPI): a session created while device 1 is current must live on device 1 -- it used to
+    be hard-wired to device 0, which put every rank's far field on GPU 0."""
+    _need_gpus(sb, 2)
+    import torch
+    from sctl_b200 import synth
+    Ns, Nt = 3001, 2003
+    r_src, _, v_src, r_trg = synth.cube(Ns, Nt, 3, 0)
+    prev = torch.cuda.current_device()
+    try:
+        torch.cuda.set_device(1)
+        free0 = torch.cuda.mem_get_info(0)[0]
+        pd = sb.ParticleDirect(np.float64)
+        assert pd.devices() == [1]
+        pd.AddSrc("S"); pd.AddTrg("T"); pd.SetAccuracy(-1)
+        pd.SetKernelS2T("S", "T", sb.Stokes3D_FxU)
+        big = np.zeros(3 * (1 << 24))  # 384 MB of target coordinates: must land on device 1
+        pd.AddTrg("big"); pd.SetTrgCoord("big", big)
+        assert torch.cuda.mem_get_info(0)[0] >= free0 - (64 << 20)
+        pd.SetSrcCoord("S", r_src); pd.SetTrgCoord("T", r_trg); pd.SetSrcDensity("S", v_src)
+        got = pd.EvalDirect(None, "T", 3)
+        assert torch.cuda.current_device() == 1  # the caller's device is left alone
+        pd.close()
+        two = sb.ParticleDirect(np.float64, devices=[1, 0])
+        assert two.devices() == [1, 0]
+        two.close()
+    finally:
+        torch.cuda.set_device(prev)
+    assert rel_err(got, cpu_oracle.eval("Stokes3D_FxU", r_src, None, v_src, r_trg)) <= 1e-12

@@ -392,6 +392,54 @@ def test_particle_direct_session(sb, cpu_oracle, dtype):
     pd.close()
 
 
+def test_particle_direct_reads_the_kernel_context_at_every_eval(sb, cpu_oracle):
+    """The reference's ParticleFMM copies the kernel object with its ctx_ptr (fmm-wrapper.txx:442-443) and dereferences
+    the pointer at every Eval, so a wavenumber changed after SetKernelS2T takes effect at the next evaluation.  The
+    session's mirrors re-read the context at every EvalDirect."""
+    from sctl_b200 import synth
+    Ns, Nt = 1500, 1200
+    r_src, _, v_src, r_trg = synth.cube(Ns, Nt, 2, 0)
+    K = sb.GenericKernel("Helmholtz3D_FxU")
+    K.SetCtxPtr(5.0)
+    pd = sb.ParticleDirect(np.float64)
+    pd.SetAccuracy(-1)
+    pd.AddSrc("H"); pd.AddTrg("W")
+    pd.SetSrcCoord("H", r_src); pd.SetSrcDensity("H", v_src); pd.SetTrgCoord("W", r_trg)
+    pd.SetKernelS2T("H", "W", K)
+    assert rel_err(pd.EvalDirect(None, "W", 2), cpu_oracle.eval("Helmholtz3D_FxU", r_src, None, v_src, r_trg, ctx=5.0)) <= 1e-12
+    K.SetCtxPtr(9.5)  # no new SetKernelS2T
+    assert rel_err(pd.EvalDirect(None, "W", 2), cpu_oracle.eval("Helmholtz3D_FxU", r_src, None, v_src, r_trg, ctx=9.5)) <= 1e-12
+    pd.close()
+
+
+def test_particle_direct_lives_on_the_current_device_and_recycles_slots(sb, cpu_oracle):
+    """A one-GPU session is created on the device that is current on the creating thread (it used to be
+    device 0 whatever the rank's GPU); explicit device lists are validated; slot numbers of deleted sources are reused,
+    so add/delete cycles beyond the C ABI's 4096 slots keep working."""
+    import torch
+    from sctl_b200 import synth
+    cur = torch.cuda.current_device()
+    pd = sb.ParticleDirect(np.float64)
+    assert pd.devices() == [cur]
+    pd.close()
+    with pytest.raises(sb.SctlCudaError):
+        sb.ParticleDirect(np.float64, devices=[sb.device_count()])  # not visible
+    with pytest.raises(sb.SctlCudaError):
+        sb.ParticleDirect(np.float64, devices=[])
+    pd = sb.ParticleDirect(np.float64, devices=[cur])
+    assert pd.devices() == [cur]
+    r_src, _, v_src, r_trg = synth.cube(300, 200, 1, 0)
+    pd.AddTrg("T"); pd.SetTrgCoord("T", r_trg); pd.SetAccuracy(-1)
+    for it in range(4200):  # more cycles than the ABI has slots
+        pd.AddSrc("S%d" % it)
+        if it % 1000 == 0 or it == 4199:
+            pd.SetSrcCoord("S%d" % it, r_src); pd.SetSrcDensity("S%d" % it, v_src)
+            pd.SetKernelS2T("S%d" % it, "T", sb.Laplace3D_FxU)
+            assert rel_err(pd.EvalDirect(None, "T", 1), cpu_oracle.eval("Laplace3D_FxU", r_src, None, v_src, r_trg)) <= 1e-12
+        pd.DeleteSrc("S%d" % it)
+    pd.close()
+
+
 @pytest.mark.parametrize("kernel", ["Helmholtz3D_FxU", "Helmholtz3D_FxdU", "HelmholtzDiff3D_FxdU"])
 def test_helmholtz_wavenumbers_cover_both_sincos_paths(sb, cpu_oracle, kernel):
     """The device sin/cos (csrc/pair_math.cuh sincos_real) has a polynomial path for |mu r| <= 1e5 (FP32: 4.5e4) and
