@@ -117,6 +117,11 @@ int sctl_cuda_kernel_matrix_device(int kernel_id, int real_bytes, int digits, in
 /* Device-side twin of approx_rsqrt<digits>(x, x > 0) on n device values (contract test, vec-test.hpp:431-465). */
 int sctl_cuda_rsqrt_device(int real_bytes, int digits, int64_t n, const void* d_x, void* d_y, void* stream);
 
+/* Every host thread that calls a host-pointer entry owns a stream, four events and (after its first small call) a 1 MB
+ * pinned + 1 MB device arena per device.  A thread that ends parks them in a process-wide pool; the next new thread
+ * takes them over; sctl_cuda_finalize() releases what is parked.  Returns how many sets are parked for `device`. */
+int sctl_cuda_idle_thread_resources(int device);
+
 /* Timings (ms, CUDA events on the call's stream) of the calling thread's last host-pointer call. */
 int sctl_cuda_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms);
 

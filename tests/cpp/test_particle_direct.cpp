@@ -47,7 +47,7 @@ template <class Real> static double rel_err(const Vector<Real>& a, const Vector<
 
 // Two source types (single layer + double layer with normals) into one velocity target set, a second target set fed by
 // one source type only, then a new density (the GMRES pattern), then changed coordinates.
-template <class Real> static void run(int n_gpus, double tol) {
+template <class Real> static void run(int n_gpus, int digits, double tol) {
   const Stokes3D_FSxU ker_m2l;
   const Stokes3D_FxU ker_sl;
   const Stokes3D_DxU ker_dl;
@@ -60,8 +60,8 @@ template <class Real> static void run(int n_gpus, double tol) {
 
   ParticleFMM<Real, 3> ref;  // CPU checker: the reference's own direct path
   sctl_cuda::ParticleDirect<Real> gpu(n_gpus);
-  ref.SetAccuracy(10);
-  gpu.SetAccuracy(10);
+  ref.SetAccuracy(digits);
+  gpu.SetAccuracy(digits);
   ref.SetKernels(ker_m2l, ker_m2l, ker_sl);
   gpu.SetKernels(ker_m2l, ker_m2l, ker_sl);
   ref.AddTrg("Velocity", ker_m2l, ker_sl);
@@ -131,6 +131,8 @@ template <class Real> static void run(int n_gpus, double tol) {
   ParticleFMM<Real, 3> ref2;
   sctl_cuda::ParticleDirect<Real> gpu2(n_gpus);
   Vector<Real> Q = rand_vec<Real>(Nsl);
+  ref2.SetAccuracy(digits);
+  gpu2.SetAccuracy(digits);
   ref2.SetKernels(lap_sl, lap_sl, lap_sl);
   ref2.AddSrc("Charge", lap_sl, lap_sl);
   gpu2.AddSrc("Charge", lap_sl, lap_sl);
@@ -160,8 +162,13 @@ template <class Real> static void run(int n_gpus, double tol) {
 
 int main(int argc, char** argv) {
   const int n_gpus = argc > 1 ? std::atoi(argv[1]) : 1;
-  run<double>(n_gpus, 1e-12);
-  run<float>(n_gpus, 1e-5);
+  // ParticleFMM's default accuracy is 10 digits (fmm-wrapper.txx:205): the device serves that request with its
+  // 4-instruction reciprocal-square-root class (error < 9e-13 per pair, zero mean), the reference's AVX-512 path with full
+  // precision, so the two agree to ~1e-11 there (kernels with rinv^5 amplify the per-pair error five-fold); at 15 digits
+  // both are at working precision and the north-star gate 1e-12 applies.
+  run<double>(n_gpus, 10, 2e-11);
+  run<double>(n_gpus, 15, 1e-12);
+  run<float>(n_gpus, 10, 1e-5);
   std::printf("%s (%d check(s) failed)\n", n_fail ? "FAIL" : "PASS", n_fail);
   return n_fail ? 1 : 0;
 }

@@ -24,7 +24,10 @@ def test_eval_matches_reference_golden(sb, golden, kernel, dtype):
         want = golden[cases.key(kernel, dtype, Ns, Nt, variant, digits)]
         assert got.dtype == want.dtype and got.shape == want.shape
         assert np.all(np.isfinite(got)), (kernel, Ns, Nt, variant)
-        assert rel_err(got, want) <= TOL[dtype], (kernel, dtype.__name__, Ns, Nt, variant, digits, rel_err(got, want))
+        # digits 10 / 11 ask for 10 / 11 digits: FP64 serves them with the 4-instruction step (rsqrt error < 9e-13, zero
+        # mean), the golden vectors come from the reference's AVX-512 path, which is at full precision there
+        tol = 4e-12 if (dtype is np.float64 and 6 <= digits <= 11) else TOL[dtype]
+        assert rel_err(got, want) <= tol, (kernel, dtype.__name__, Ns, Nt, variant, digits, rel_err(got, want))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -159,9 +162,12 @@ def test_rsqrt_contract_on_device(sb):
         sb.rsqrt_device(dx, dy, digits=digits)
         y = dy.cpu().numpy()
         d = 15 if digits == -1 else digits
-        bound = {4: 2.0 ** -11, 7: 2.0 ** -22, 10: 5e-16, 11: 5e-16, 12: 5e-16}.get(digits, max(10.0 ** -d, 5e-16))  # full precision: within ~2 ulp
+        # 6..11: one first-order step, max error 8.6e-13 (tools/seed_error.py); 12 and up: full precision, within ~2 ulp
+        bound = {4: 2.0 ** -11, 7: 2.0 ** -22, 10: 9e-13, 11: 9e-13, 12: 5e-16}.get(digits, max(10.0 ** -d, 5e-16))
         err = np.abs(y[:20001] - exact) / exact
         assert err.max() < bound, (digits, err.max())
+        if digits in (10, 11):  # the step's line is centred on the seed's residual distribution: no systematic bias
+            assert abs(((y[:20001] - exact) / exact).mean()) < 5e-14
         assert np.all(y[20001:] == 0), y[20001:]  # zero, negative and subnormal inputs are masked to exactly 0
     xf = np.concatenate([10.0 ** np.linspace(-37, 38, 20001), [0.0, -1.0, 1e-45, 1e-39]]).astype(np.float32)
     exf = 1 / np.sqrt(xf[:20001].astype(np.float64))
