@@ -195,6 +195,30 @@ int sctl_cuda_near_set_targets(sctl_cuda_near_t h, int64_t n_trg, const int64_t*
                                const int64_t* near_scatter_index);
 int sctl_cuda_near_apply_accumulate(sctl_cuda_near_t h, const void* F, int64_t nF, void* U /* n_trg*K1, accumulated into */, int64_t nU);
 
+/* ---- One BoundaryIntegralOp apply as one device-side pipeline (SURVEY section 8 f1 + f3) ------------------------
+ * BoundaryIntegralOp::ComputePotential = ComputeFarField + ComputeNearInterac (boundary_integral.txx:716-722,
+ * 1248-1309, 1311-1383), once per GMRES iteration with fixed geometry.  The session borrows a direct session (one
+ * interaction src -> trg, coordinates set) and, optionally, a near-field session on the direct session's first GPU
+ * (matrix and target tables set); both must outlive it and must not be used while an apply is running.
+ *   create   wts_far[Nsrc]: quadrature weights of the far-field nodes (:1270-1283); trg_normal_dot_prod with Xn_trg[Ntrg*3]
+ *            contracts the kernel's 3*KDIM1_ target components with the target normals (:1293-1303)
+ *   apply    U[Ntrg*KDIM1_] = far field of (F_far * wts_far) + near correction of F.  F: the node density (Nnodes*K0);
+ *            F_far_nodes: the density at the far-field nodes where the element list has a far-field density operator
+ *            (GetFarFieldDensity, :1267), or NULL / 0 when the far-field nodes are the nodes (every element list of the
+ *            reference tree, :527-529) and F itself is used.  Per apply the density goes up once per GPU and U comes down
+ *            once; F * wts, the normal contraction and the per-target accumulation are device kernels; the near-field GEMV
+ *            (HBM-bound) runs on its own stream beside the far-field launches (FP64-bound); the shards of a multi-GPU far
+ *            field are collected on the first GPU with peer copies.  Same arithmetic and summation order as
+ *            sctl_cuda_direct_eval followed by sctl_cuda_near_apply_accumulate (bit-identical without trg_normal_dot_prod).
+ *   last_timing  device times of the last apply (ms): until the far field has landed on the first GPU; the tail behind it
+ *            (contraction, accumulation); the whole apply including the download. */
+typedef struct sctl_cuda_bio_s* sctl_cuda_bio_t;
+int sctl_cuda_bio_create(sctl_cuda_direct_t far, int src, int trg, sctl_cuda_near_t near /* may be NULL */, int trg_normal_dot_prod,
+                         const void* wts_far, int64_t n_wts, const void* Xn_trg, int64_t n_Xn_trg, sctl_cuda_bio_t* out);
+int sctl_cuda_bio_destroy(sctl_cuda_bio_t h);
+int sctl_cuda_bio_apply(sctl_cuda_bio_t h, int digits, const void* F, int64_t nF, const void* F_far_nodes, int64_t nF_far, void* U, int64_t nU);
+int sctl_cuda_bio_last_timing(sctl_cuda_bio_t h, double* far_ms, double* tail_ms, double* total_ms);
+
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
  *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64;
  *                       FP32 per "const_fp32": 0 never, 1 always, -1 (default) for Nt >= 2^17 and every kernel but

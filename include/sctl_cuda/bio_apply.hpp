@@ -12,6 +12,12 @@
 // NearBlocks::SubtractDirect for the "KNearSubtract" phase; this class is what a GMRES iteration calls.  A maintainer
 // constructs it at the end of BoundaryIntegralOp::Setup from members that already exist;
 // tests/cpp/test_near_blocks_ref.cpp does exactly that against the reference's own ComputePotential.
+//
+// ComputePotential runs the whole apply as one device-side pipeline (sctl_cuda_bio_apply, csrc/bio_session.inc): the
+// density goes up once per GPU, F * wts and the normal contraction are device kernels, the near-field GEMV runs beside the
+// far-field launches on its own stream, the shards of a multi-GPU far field are collected on the first GPU, U comes down
+// once.  ComputePotentialStaged is the same apply from the two sessions' host-array entries (far field down, up again for
+// the accumulation, down again) -- kept as the cross-check: without trg_normal_dot_prod the two are bit-identical.
 // Works with any vector type that has Dim(), ReInit(n) and operator[] (sctl::Vector<Real>, sctl_cuda::Vector<Real>).
 #ifndef SCTL_CUDA_BIO_APPLY_HPP_
 #define SCTL_CUDA_BIO_APPLY_HPP_
@@ -52,9 +58,15 @@ template <class Real> class BioApply {
     far_.SetTrgCoord("Trg", Xtrg);
   }
 
+  ~BioApply() { sctl_cuda_bio_destroy(bio_); }
+
   // Hands over the near-field session (operator set, SubtractDirect done or K_near uploaded after the CPU did it, SetTargets
   // called).  Without one, ComputePotential is the far field alone (element lists with dist_far = 0).
-  void SetNear(std::unique_ptr<NearBlocks<Real>> near) { near_ = std::move(near); }
+  void SetNear(std::unique_ptr<NearBlocks<Real>> near) {
+    sctl_cuda_bio_destroy(bio_);  // the pipeline is rebuilt around the new near-field session at the next apply
+    bio_ = nullptr;
+    near_ = std::move(near);
+  }
   NearBlocks<Real>* Near() { return near_.get(); }
 
   Long SrcCount() const { return Nsrc_; }
@@ -65,6 +77,30 @@ template <class Real> class BioApply {
   // element list has a far-field density operator (GetFarFieldDensity, :1267); empty (the default of every element list in
   // the reference tree, :527-529) means the far-field nodes are the nodes and F itself is used (:1277-1283).
   template <class VecOut, class VecIn> void ComputePotential(VecOut& U, const VecIn& F, const VecIn& F_far_nodes = VecIn()) {
+    SCTL_CUDA_ASSERT((F_far_nodes.Dim() ? F_far_nodes.Dim() : F.Dim()) == Nsrc_ * k0_);
+    const Integer k1r = TrgDof();
+    if (U.Dim() != Ntrg_ * k1r) U.ReInit(Ntrg_ * k1r);
+    if (!bio_) {
+      if (sctl_cuda_bio_create(far_.Handle(), far_.SrcSlot("Src"), far_.TrgSlot("Trg"), near_ ? near_->Handle() : nullptr, ndot_ ? 1 : 0, Nsrc_ ? wts_.data() : nullptr, Nsrc_,
+                               ndot_ && Ntrg_ ? nrm_.data() : nullptr, ndot_ ? Ntrg_ * 3 : 0, &bio_))
+        detail::die("sctl_cuda_bio_create");
+    }
+    far_.RefreshContexts("Trg");
+    const Integer digits = far_.Accuracy();
+    if (sctl_cuda_bio_apply(bio_, (int)(digits >= 16 ? -1 : digits), F.Dim() ? &F[0] : nullptr, F.Dim(), F_far_nodes.Dim() ? &F_far_nodes[0] : nullptr, F_far_nodes.Dim(),
+                            U.Dim() ? &U[0] : nullptr, U.Dim()))
+      detail::die("sctl_cuda_bio_apply");
+  }
+
+  // Device times of the last ComputePotential (ms): until the far field is complete on the first GPU, the tail behind it,
+  // and the whole apply including the download of U.
+  void LastTiming(double& far_ms, double& tail_ms, double& total_ms) const {
+    far_ms = tail_ms = total_ms = 0;
+    if (bio_) sctl_cuda_bio_last_timing(bio_, &far_ms, &tail_ms, &total_ms);
+  }
+
+  // The same apply through the two sessions' host-array entries, phase after phase (the cross-check of the pipeline above).
+  template <class VecOut, class VecIn> void ComputePotentialStaged(VecOut& U, const VecIn& F, const VecIn& F_far_nodes = VecIn()) {
     const VecIn& Fsrc = F_far_nodes.Dim() ? F_far_nodes : F;
     SCTL_CUDA_ASSERT(Fsrc.Dim() == Nsrc_ * k0_);
     if (F_far_.Dim() != Nsrc_ * k0_) F_far_.ReInit(Nsrc_ * k0_);
@@ -90,6 +126,7 @@ template <class Real> class BioApply {
  private:
   ParticleDirect<Real> far_;
   std::unique_ptr<NearBlocks<Real>> near_;
+  sctl_cuda_bio_t bio_ = nullptr;  // borrows far_ and near_: destroyed before them
   bool ndot_;
   Integer k0_, k1_;
   Long Nsrc_, Ntrg_;

@@ -94,6 +94,8 @@ template <class Real> class NearBlocks {
     if (sctl_cuda_near_apply_accumulate(h_, F.Dim() ? &F[0] : nullptr, F.Dim(), U.Dim() ? &U[0] : nullptr, U.Dim())) detail::die("sctl_cuda_near_apply_accumulate");
   }
 
+  sctl_cuda_near_t Handle() const { return h_; }
+
  private:
   sctl_cuda_near_t h_;
 };

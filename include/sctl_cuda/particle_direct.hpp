@@ -148,6 +148,26 @@ template <class Real, Integer DIM = 3> class ParticleDirect {
   }
   template <class Vec> void Eval(Vec& U, const std::string& trg_name) const { EvalDirect(U, trg_name); }
 
+  // For the layers built on top (bio_apply.hpp): the C-ABI session and the slot numbers behind the names
+  sctl_cuda_direct_t Handle() const { return h_; }
+  int SrcSlot(const std::string& name) const {
+    auto it = src_.find(name);
+    SCTL_CUDA_ASSERT(it != src_.end());
+    return it->second;
+  }
+  int TrgSlot(const std::string& name) const {
+    auto it = trg_.find(name);
+    SCTL_CUDA_ASSERT(it != trg_.end());
+    return it->second.slot;
+  }
+  Integer Accuracy() const { return digits_; }
+  // pushes the kernels' current contexts (wavenumbers) into the session, as EvalDirect does before it evaluates
+  void RefreshContexts(const std::string& trg_name) const {
+    const int slot = TrgSlot(trg_name);
+    for (const S2T& e : s2t_ctx_)
+      if (e.trg == slot) push_s2t(e);
+  }
+
  private:
   struct Trg {
     int slot;

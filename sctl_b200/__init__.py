@@ -51,6 +51,8 @@ def load_library():
     L.sctl_cuda_kernel_matrix_device.argtypes = [i, i, i, i64, i64, vp, vp, vp, vp, i64, vp, i64, vp]
     L.sctl_cuda_rsqrt_device.argtypes = [i, i, i64, vp, vp, vp]
     L.sctl_cuda_last_timing.argtypes = [dp, dp, dp]
+    L.sctl_cuda_idle_thread_resources.argtypes = [i]
+    L.sctl_cuda_idle_thread_resources.restype = i
     L.sctl_cuda_last_plan.argtypes = [ip, ip, ip, ip, ip, ip, dp]
     L.sctl_cuda_fma_peak.argtypes = [i, C.c_double, dp]
     L.sctl_cuda_set_option.argtypes = [C.c_char_p, i64]
@@ -75,6 +77,10 @@ def load_library():
     L.sctl_cuda_near_set_targets.argtypes = [vp, i64, p64, p64, i64, p64]
     L.sctl_cuda_near_apply_accumulate.argtypes = [vp, vp, i64, vp, i64]
     L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
+    L.sctl_cuda_bio_create.argtypes = [vp, i, i, vp, i, vp, i64, vp, i64, C.POINTER(vp)]
+    L.sctl_cuda_bio_destroy.argtypes = [vp]
+    L.sctl_cuda_bio_apply.argtypes = [vp, i, vp, i64, vp, i64, vp, i64]
+    L.sctl_cuda_bio_last_timing.argtypes = [vp, dp, dp, dp]
     _lib = L
     return L
 
@@ -566,4 +572,84 @@ class NearBlocks:
         if not isinstance(U, np.ndarray) or U.dtype != self._dtype or not U.flags.c_contiguous:
             raise SctlCudaError("U must be a contiguous %s array (it is accumulated into)" % np.dtype(self._dtype).name)
         _check(load_library().sctl_cuda_near_apply_accumulate(self._h, _np_ptr(F), F.size, _np_ptr(U.reshape(-1)), U.size))
+        return U
+
+
+class BioApply:
+    """One ``BoundaryIntegralOp::ComputePotential`` (boundary_integral.txx:716-722: ``ComputeFarField`` :1248-1309 +
+    ``ComputeNearInterac`` :1311-1383) as one device-side pipeline over ``sctl_cuda_bio_*``: the density goes up once per
+    GPU, ``F * wts_far`` and the target-normal contraction are device kernels, the near-field GEMV runs beside the
+    far-field launches, the shards of a multi-GPU far field are collected on the first GPU, ``U`` comes down once.
+    Mirrors ``sctl_cuda::BioApply<Real>`` (include/sctl_cuda/bio_apply.hpp); ``compute_potential_staged`` is the same apply
+    phase after phase through the two sessions' host-array entries (the cross-check)."""
+
+    def __init__(self, kernel, X_far, Xn_far, wts_far, Xtrg, Xn_trg=None, digits=11, dtype=np.float64, n_gpus=1, devices=None, near=None):
+        self.kernel = kernel if isinstance(kernel, GenericKernel) else GenericKernel(kernel)
+        self._dtype = np.dtype(dtype).type
+        c = lambda a: None if a is None else np.ascontiguousarray(a, dtype=self._dtype).reshape(-1)
+        self._wts, self._nrm = c(wts_far), c(Xn_trg)
+        self.ndot = Xn_trg is not None
+        self.k0, self.k1 = self.kernel.SrcDim(), self.kernel.TrgDim()
+        if self.ndot and self.k1 % 3:
+            raise SctlCudaError("trg_normal_dot_prod needs a kernel whose target dimension is a multiple of 3")
+        self.k1r = self.k1 // 3 if self.ndot else self.k1
+        self.Nsrc, self.Ntrg = c(X_far).size // 3, c(Xtrg).size // 3
+        self.far = ParticleDirect(dtype, n_gpus=n_gpus, devices=devices)
+        self.far.SetAccuracy(digits)
+        self.far.AddSrc("Src"); self.far.AddTrg("Trg")  # the names BoundaryIntegralOp uses (:573-575)
+        self.far.SetKernelS2T("Src", "Trg", self.kernel)
+        self.far.SetSrcCoord("Src", X_far, Xn_far)
+        self.far.SetTrgCoord("Trg", Xtrg)
+        self.near = near
+        self._h = C.c_void_p()
+
+    def set_near(self, near):
+        self.close_pipeline()
+        self.near = near
+
+    def close_pipeline(self):
+        if self._h:
+            load_library().sctl_cuda_bio_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def close(self):
+        self.close_pipeline()
+        self.far.close()
+
+    def __del__(self):
+        try:
+            self.close_pipeline()
+        except Exception:
+            pass
+
+    def compute_potential(self, F, F_far_nodes=None, U=None):
+        L = load_library()
+        F = np.ascontiguousarray(F, dtype=self._dtype).reshape(-1)
+        Ff = None if F_far_nodes is None else np.ascontiguousarray(F_far_nodes, dtype=self._dtype).reshape(-1)
+        if not self._h:
+            _check(L.sctl_cuda_bio_create(self.far._h, self.far._src["Src"], self.far._trg["Trg"], self.near._h if self.near is not None else None, int(self.ndot),
+                                          _np_ptr(self._wts), self._wts.size, _np_ptr(self._nrm), 0 if self._nrm is None else self._nrm.size, C.byref(self._h)))
+        for st, k in self.far._s2t.items():
+            self.far._push_s2t(st, k)
+        n = self.Ntrg * self.k1r
+        if U is None or not isinstance(U, np.ndarray) or U.size != n or U.dtype != self._dtype or not U.flags.c_contiguous:
+            U = np.zeros(n, dtype=self._dtype)
+        d = self.far._digits
+        _check(L.sctl_cuda_bio_apply(self._h, -1 if d >= 16 else d, _np_ptr(F), F.size, _np_ptr(Ff), 0 if Ff is None else Ff.size, _np_ptr(U.reshape(-1)), n))
+        return U
+
+    def last_timing(self):
+        a, b, c = C.c_double(), C.c_double(), C.c_double()
+        _check(load_library().sctl_cuda_bio_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"far_ms": a.value, "tail_ms": b.value, "total_ms": c.value}
+
+    def compute_potential_staged(self, F, F_far_nodes=None):
+        F = np.ascontiguousarray(F, dtype=self._dtype).reshape(-1)
+        Fs = F if F_far_nodes is None else np.ascontiguousarray(F_far_nodes, dtype=self._dtype).reshape(-1)
+        self.far.SetSrcDensity("Src", (Fs.reshape(-1, self.k0) * self._wts[:, None]).reshape(-1))  # F_far <-- F * wts_far (:1270-1283)
+        U = self.far.EvalDirect(None, "Trg", self.k1)
+        if self.ndot:  # (:1293-1301)
+            U = np.ascontiguousarray((U.reshape(self.Ntrg, self.k1r, 3) * self._nrm.reshape(self.Ntrg, 1, 3)).sum(axis=2).reshape(-1))
+        if self.near is not None:
+            self.near.apply_accumulate(F, U)
         return U

@@ -908,6 +908,7 @@ constexpr double MULTI_GPU_MIN_PAIRS = 1.0e9;
 
 #include "direct_session.inc"
 #include "near_session.inc"
+#include "bio_session.inc"
 
 // =================================================================================================
 // C ABI

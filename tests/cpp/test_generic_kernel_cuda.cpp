@@ -308,6 +308,16 @@ template <class R> static void session_layers() {
       }
     CHECK(e0 <= tol * m1);
     CHECK(e1 <= tol * m1);
+    // the pipeline (one upload, near GEMV beside the far field, one download) against the same apply staged through the two
+    // sessions' host-array entries: same arithmetic, same order -> identical bits
+    Vector<R> Ustaged;
+    bio.ComputePotentialStaged(Ustaged, F);
+    Long n_diff = 0;
+    for (Long i = 0; i < Nt * 3; i++) n_diff += (Ustaged[i] != Ubio[i]);
+    CHECK(n_diff == 0);
+    double t_far = 0, t_tail = 0, t_all = 0;
+    bio.LastTiming(t_far, t_tail, t_all);
+    CHECK(t_all > 0 && t_far > 0);
   }
 }
 

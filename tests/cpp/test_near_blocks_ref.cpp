@@ -180,6 +180,10 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
   // the near correction removes them, so the whole apply agrees with the reference to ~1e-12 (measured 3e-13 .. 8e-13, profiles/r2_near_blocks_vs_reference.txt) -- a hundredth of the accuracy
   // BoundaryIntegralOp was asked for.  K_near and the near-field potential above are still gated at full precision.
   const double tol_apply = sizeof(Real) == 8 ? std::max(tol, 5e-12) : tol;
+  Vector<Real> Ustaged;
+  bio.ComputePotentialStaged(Ustaged, F);  // the same apply phase after phase through the two sessions' host-array entries
+  const double eS = rel_err(Ubio, Ustaged);
+  CHECK(ndot ? eS <= (sizeof(Real) == 8 ? 1e-14 : 1e-6) : eS == 0, "%s: the pipeline differs from the staged apply by %.3e", what, eS);
   const double eB = rel_err(Ubio, U);
   CHECK(eB <= tol_apply, "%s: BioApply::ComputePotential differs from the reference's ComputePotential by %.3e", what, eB);
   if (timing) {  // one apply with a new density: reference (CPU, far + near) against BioApply (GPU)
@@ -187,14 +191,20 @@ template <class Real, class Kernel> static void run(const char* what, bool ndot,
     auto t0 = std::chrono::steady_clock::now();
     op.ComputePotential(U, F);
     const double t_ref = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    double t_gpu = 1e30;
+    double t_gpu = 1e30, t_staged = 1e30;
     for (int rep = 0; rep < 3; rep++) {
       t0 = std::chrono::steady_clock::now();
-      bio.ComputePotential(Utot, F);  // F * wts, far field, near correction; only F and U cross PCIe
+      bio.ComputePotential(Utot, F);  // one upload of F, one download of U; everything between them on the device
       t_gpu = std::min(t_gpu, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+      t0 = std::chrono::steady_clock::now();
+      bio.ComputePotentialStaged(Ustaged, F);  // round 1's apply: the two sessions one after the other from host arrays
+      t_staged = std::min(t_staged, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
     }
-    std::printf("%-24s %ld nodes, %ld near pairs, K_near %.2f GB: reference ComputePotential %.4f s on %d host threads, BioApply %.4f s per apply (%.0fx)\n", what, (long)N,
-                (long)Nnear, op.K_near.Dim() * sizeof(Real) * 1e-9, t_ref, omp_get_max_threads(), t_gpu, t_ref / t_gpu);
+    double t_far = 0, t_tail = 0, t_all = 0;
+    bio.ComputePotential(Utot, F);
+    bio.LastTiming(t_far, t_tail, t_all);
+    std::printf("%-24s %ld nodes, %ld near pairs, K_near %.2f GB: reference ComputePotential %.4f s on %d host threads, BioApply %.4f s per apply (%.0fx); staged through the two sessions %.4f s; device times: far field (+ near GEMV beside it) %.3f ms, tail %.3f ms, whole apply %.3f ms\n", what, (long)N,
+                (long)Nnear, op.K_near.Dim() * sizeof(Real) * 1e-9, t_ref, omp_get_max_threads(), t_gpu, t_ref / t_gpu, t_staged, t_far, t_tail, t_all);
   }
   const double eT = rel_err(Utot, U);
   CHECK(eT <= tol_apply, "%s: far + near potential differs from the reference's ComputePotential by %.3e", what, eT);

@@ -107,3 +107,30 @@ def test_particle_direct_follows_the_current_device(sb, cpu_oracle):
     finally:
         torch.cuda.set_device(prev)
     assert rel_err(got, cpu_oracle.eval("Stokes3D_FxU", r_src, None, v_src, r_trg)) <= 1e-12
+
+
+def test_bio_apply_pipeline_two_gpus(sb, cpu_oracle):
+    """The whole BoundaryIntegralOp apply with the far field sharded over 2 GPUs: the shards are collected on the first GPU
+    (peer copies), the near accumulation runs there; agrees with the 1-GPU pipeline to rounding and with the staged apply."""
+    _need_gpus(sb, 2)
+    from sctl_b200 import synth
+    from test_gpu_near import block_list, near_target_tables
+    kernel, k0, k1 = "Stokes3D_FxU", 3, 3
+    tab, n_nodes, n_far, n_near, K_len = block_list(60, k0, k1, seed=11)
+    Ntrg = 40003  # ragged shards
+    cnt, dsp, scatter = near_target_tables(Ntrg, n_near, seed=3)
+    X_far, Xn_far, _, Xtrg = synth.cube(n_nodes, Ntrg, k0, 3)
+    wts = 0.01 + 0.001 * synth.splitmix_u01(32, n_nodes)
+    K_near = synth.splitmix_u01(22, K_len) - 0.5
+    F = synth.splitmix_u01(41, n_nodes * k0) - 0.5
+    res = []
+    for n in (1, 2):
+        near = sb.NearBlocks(sb.KERNELS[kernel], *tab)
+        near.set_matrix(K_near)
+        near.set_targets(cnt, dsp, scatter)
+        bio = sb.BioApply(sb.KERNELS[kernel], X_far, Xn_far, wts, Xtrg, None, digits=-1, n_gpus=n, near=near)
+        res.append(bio.compute_potential(F))
+        assert np.array_equal(res[-1], bio.compute_potential_staged(F))
+        bio.close()
+        near.close()
+    assert rel_err(res[0], res[1]) <= 1e-13

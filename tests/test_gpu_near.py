@@ -178,3 +178,68 @@ def test_near_apply_accumulate_matches_the_reference_tail(sb, kernel, dtype):
     # plain apply still works after the tables were (re)set
     assert np.array_equal(nb.apply(F), U_near)
     nb.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kernel,ndot", [("Stokes3D_FxU", False), ("Laplace3D_DxU", False), ("Laplace3D_FxdU", True), ("Stokes3D_FxT", True)])
+def test_bio_apply_pipeline_matches_the_staged_apply_and_the_oracle(sb, cpu_oracle, kernel, ndot, dtype):
+    """sctl_cuda_bio_apply (csrc/bio_session.inc): BoundaryIntegralOp::ComputePotential (boundary_integral.txx:716-722) as one
+    device-side pipeline -- F * wts, far field, normal contraction, near GEMV beside the far field, per-target accumulation,
+    one upload and one download -- against (a) the same apply staged through the two sessions' host-array entries
+    (bit-identical without trg_normal_dot_prod) and (b) the CPU oracle's Eval plus the numpy restatement of the near loops."""
+    from oracle import near_blocks as nbo
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    k1r = k1 // 3 if ndot else k1
+    tab, n_nodes, n_far, n_near, K_len = block_list(40, k0, k1r, seed=5)
+    Ntrg = 517
+    cnt, dsp, scatter = near_target_tables(Ntrg, n_near, seed=9)
+    X_far, Xn_far, _, Xtrg = synth.cube(n_nodes, Ntrg, k0, 3, dtype=dtype)
+    Xn_trg = (synth.splitmix_u01(31, Ntrg * 3) - 0.5).astype(dtype) if ndot else None
+    wts = (0.01 + 0.001 * synth.splitmix_u01(32, n_nodes)).astype(dtype)
+    K_near = (synth.splitmix_u01(22, K_len) - 0.5).astype(dtype)
+    near = sb.NearBlocks(sb.KERNELS[kernel], *tab, dtype=dtype, trg_normal_dot_prod=ndot)
+    near.set_matrix(K_near)
+    near.set_targets(cnt, dsp, scatter)
+    bio = sb.BioApply(sb.KERNELS[kernel], X_far, Xn_far, wts, Xtrg, Xn_trg, digits=-1, dtype=dtype, near=near)
+    tol = 1e-12 if dtype == np.float64 else 2e-5
+    U = None
+    for it in range(3):  # a GMRES loop: new density, same geometry, the result array reused
+        F = (synth.splitmix_u01(40 + it, n_nodes * k0) - 0.5).astype(dtype)
+        U = bio.compute_potential(F, U=U)
+        staged = bio.compute_potential_staged(F)
+        if ndot:
+            assert rel_err(U, staged) <= (1e-14 if dtype == np.float64 else 1e-6)
+        else:
+            assert np.array_equal(U, staged)
+        f64 = lambda a: None if a is None else a.astype(np.float64)
+        far = cpu_oracle.eval(kernel, f64(X_far), f64(Xn_far) if nd else None, (f64(F).reshape(-1, k0) * f64(wts)[:, None]).reshape(-1), f64(Xtrg))
+        if ndot:
+            far = (far.reshape(Ntrg, k1r, 3) * f64(Xn_trg).reshape(Ntrg, 1, 3)).sum(axis=2).reshape(-1)
+        want = nbo.near_accumulate(k1r, far, nbo.near_apply(k0, k1r, tab, f64(K_near), f64(F), n_near * k1r), cnt, dsp, scatter)
+        assert rel_err(U, want) <= tol, (kernel, ndot, it, rel_err(U, want))
+    t = bio.last_timing()
+    assert t["total_ms"] > 0 and t["far_ms"] > 0
+    # a far-field density that differs from the node density (GetFarFieldDensity, :1267)
+    Ffar = (synth.splitmix_u01(77, n_nodes * k0) - 0.5).astype(dtype)
+    got = bio.compute_potential(F, F_far_nodes=Ffar)
+    staged = bio.compute_potential_staged(F, F_far_nodes=Ffar)
+    assert np.array_equal(got, staged) if not ndot else rel_err(got, staged) <= (1e-14 if dtype == np.float64 else 1e-6)
+    # far field alone (element lists with dist_far = 0: no near list)
+    bio.set_near(None)
+    got = bio.compute_potential(F)
+    staged = bio.compute_potential_staged(F)
+    assert np.array_equal(got, staged) if not ndot else rel_err(got, staged) <= (1e-14 if dtype == np.float64 else 1e-6)
+    # refusals: sizes that do not fit, a near-field session for another target count
+    with pytest.raises(sb.SctlCudaError, match="density"):
+        bio.compute_potential(F[:-1])
+    near2 = sb.NearBlocks(sb.KERNELS[kernel], *tab, dtype=dtype, trg_normal_dot_prod=ndot)
+    near2.set_matrix(K_near)
+    c2, d2, s2 = near_target_tables(Ntrg + 1, n_near, seed=9)
+    near2.set_targets(c2, d2, s2)
+    bio.set_near(near2)
+    with pytest.raises(sb.SctlCudaError, match="targets"):
+        bio.compute_potential(F)
+    bio.close()
+    near.close()
+    near2.close()

@@ -471,3 +471,40 @@ def test_helmholtz_wavenumbers_cover_both_sincos_paths(sb, cpu_oracle, kernel):
     f = lambda a: None if a is None else a.astype(np.float32)
     got32 = K.Eval(None, f(r_trg), f(r_src), f(n_src), f(v_src), dtype=np.float32)
     assert np.all(np.isfinite(got32))
+
+
+def test_thread_resources_are_handed_on_not_leaked(sb, cpu_oracle):
+    """Every host thread gets its own stream, events and (for small calls) a pinned + device arena.  Threads that end park
+    them in a pool, new threads take them over, finalize releases them (they used to leak, 1 MB of pinned memory
+    per finished thread).  Twelve short-lived threads, one after the other, leave ONE parked set behind, not twelve."""
+    import threading
+    import torch
+    from sctl_b200 import synth
+    L = sb.load_library()
+    dev = torch.cuda.current_device()
+    r_src, _, v_src, r_trg = synth.cube(200, 150, 3, 0)
+    want = cpu_oracle.eval("Stokes3D_FxU", r_src, None, v_src, r_trg)
+    L.sctl_cuda_finalize()
+    assert L.sctl_cuda_idle_thread_resources(dev) == 0
+    errs = []
+
+    def work():
+        torch.cuda.set_device(dev)
+        got = sb.Stokes3D_FxU.Eval(None, r_trg, r_src, None, v_src)  # small call: arena path
+        errs.append(rel_err(got, want))
+
+    for _ in range(12):
+        t = threading.Thread(target=work)
+        t.start()
+        t.join()
+    assert len(errs) == 12 and max(errs) <= 1e-12
+    assert L.sctl_cuda_idle_thread_resources(dev) == 1
+    ts = [threading.Thread(target=work) for _ in range(4)]  # concurrent threads each need their own set
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert 1 <= L.sctl_cuda_idle_thread_resources(dev) <= 4 and max(errs) <= 1e-12
+    L.sctl_cuda_finalize()
+    assert L.sctl_cuda_idle_thread_resources(dev) == 0
+    assert rel_err(sb.Stokes3D_FxU.Eval(None, r_trg, r_src, None, v_src), want) <= 1e-12  # the library re-initialises itself
