@@ -102,8 +102,31 @@ def device_count():
     return int(load_library().sctl_cuda_device_count())
 
 
+def _prefer_newest_nccl():
+    """The C library dlopen()s ``libnccl.so.2`` when it is asked to shard over several GPUs.  A process can only hold ONE
+    library of that soname: if the system's NCCL is loaded first and torch is imported afterwards, torch binds to it and may
+    miss symbols of the newer NCCL it ships (``undefined symbol: ncclDevCommCreate``).  So before the C library loads NCCL,
+    the copy that the Python environment ships (the ``nvidia-nccl`` wheel torch depends on) is loaded, if there is one and
+    nothing has loaded NCCL yet; both users then share it."""
+    import sys
+    if "torch" in sys.modules:
+        return  # torch has loaded its own NCCL already; the C library's dlopen finds that one by soname
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except (ImportError, OSError, ValueError):
+        pass
+
+
 def init(n_gpus=0):
     """sctl_cuda_init: shard host-pointer calls over ``n_gpus`` GPUs of this process (0 = all visible)."""
+    if int(n_gpus) != 1:
+        _prefer_newest_nccl()
     _check(load_library().sctl_cuda_init(int(n_gpus)))
     return int(load_library().sctl_cuda_num_gpus())
 
