@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
