@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read here, no GPU needed) or an ncu launch-list csv into markdown for profiles/.
 
-    python tools/ncu_summary.py rep  gpurun_out/prof.ncu-rep      > profiles/xxx.md
+    python tools/ncu_summary.py rep  gpurun_out/prof.ncu-rep      > profiles/xxx.md     (or the report's raw-page csv)
     python tools/ncu_summary.py list gpurun_out/launches.csv      > profiles/yyy.md
 """
 import csv
@@ -31,7 +31,11 @@ KEYS = [
 
 
 def rep(path):
-    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a .ncu-rep is read with ncu itself; a .csv is the `--page raw --csv` dump of a report made on the GPU box
+    if path.endswith(".csv"):
+        out = open(path).read()
+    else:
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     print("# ncu --set full summary: `%s`\n" % path.split("/")[-1])
