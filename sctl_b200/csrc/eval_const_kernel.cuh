@@ -21,6 +21,14 @@
 
 #include "pair_math.cuh"
 
+// Tuning switches (tools/ab_build.sh builds variants to measure the difference):
+//   SCTL_CUDA_CONST_HOIST  -1: per kernel (ConstHoist below); 0 / 1: the refinement's loop-invariant operands are
+//                          literals / kernel arguments for every FP64 kernel
+//   SCTL_CUDA_F32X2        (pair_math.cuh) 1: FP32 pair loops on packed values; 0: scalar
+#ifndef SCTL_CUDA_CONST_HOIST
+#define SCTL_CUDA_CONST_HOIST -1
+#endif
+
 namespace sctl_cuda {
 
 constexpr int CONST_PACK_BYTES = 64 * 1024 - 1024;  // leave room for the compiler's own bank-3 constants
@@ -42,8 +50,18 @@ template <class Real> struct ConstEvalArgs {
   int bank_off;       // first Real of this launch's bank inside c_src_pack (multi-bank streaming, see below)
   int bits_off;       // first 32-bit word of this launch's coincidence bits inside c_src_pack (one bit per CTA), -1: none
   int allow_unmasked; // this call ran the coincidence probe: c_eval_must_mask is meaningful
+  int zero;           // 0, as a value ptxas cannot fold: the seed's low word (see the kernel)
   Real scale;
   Real ctx0;          // kernel context by value (Helmholtz wavenumber)
+  Real rsq_k;         // rsq_poly_k<RSQ>(): the refinement's register-resident coefficient
+};
+
+// Whether the FP64 loop keeps the rsqrt refinement's loop-invariant operands in registers (see the kernel).  It removes
+// 10 IMAD.MOV per 8 pairs from the loop, but those issue in the FP64 pipe's shadow and what decides is how ptxas then
+// schedules the loop: measured on B200 (profiles/r2b_ab_rate.md, 2^19 x 2^19, digits -1 / 11) Laplace3D_FxU +1.9 % / +0.6 %,
+// Stokes3D_FxU -0.3 % / -1.0 %, Stokes3D_DxU -1.6 % / -0.2 %.  So: only where the pair is short.
+template <class Real, int KID> struct ConstHoist {
+  static constexpr bool value = SCTL_CUDA_CONST_HOIST < 0 ? (sizeof(Real) == 8 && KID == LAPLACE3D_FXU) : (SCTL_CUDA_CONST_HOIST != 0);
 };
 
 template <class Real, int KID> constexpr int const_chunk_records() { return CONST_PACK_BYTES / (RecTraits<Real, KID>::REC * (int)sizeof(Real)); }
@@ -83,6 +101,33 @@ template <class Real, int KID> inline ConstGeom const_geometry(int64_t Ns, int64
   return g;
 }
 
+// U sources x T targets per iteration, unrolled by hand (not #pragma unroll U) so that every unrolled pair has its own
+// `lo` operand; the remainder (n % U sources) runs one source at a time.  `src` and `n` are warp-uniform: the records
+// are read with LDCU into uniform registers.  V is the type a pair is computed in: Real, or f32x2 (two targets per
+// value, packed FP32 instructions with the record's scalars as broadcast uniform operands; pair_math.cuh).
+template <class V, class Real, int KID, int T, int RSQ, int U, bool MASK>
+__device__ __forceinline__ void const_pair_loop(V (&acc)[T][KerTraits<KID>::K1], const V (&xt)[T][3], const Real* src, int n, V ctx0,
+                                                const int (&lo)[U][T], V k) {
+  constexpr int REC = RecTraits<Real, KID>::REC;
+  int s = 0;
+  for (; s + U <= n; s += U) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const Real* rec = src + (s + u) * REC;  // uniform address: LDCU into uniform registers
+#pragma unroll
+      for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, ctx0, lo[u][j], k);
+    }
+  }
+  for (; s < n; s++) {
+    const Real* rec = src + s * REC;
+#pragma unroll
+    for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, ctx0, lo[0][j], k);
+  }
+}
+
+// FP32 pair loops run on packed values (two targets each) where the kernel has no transcendental part
+template <class Real, int KID, int T> __host__ __device__ constexpr bool const_packed() { return SCTL_CUDA_F32X2 && sizeof(Real) == 4 && !KerNeedsCtx<KID>::value && T % 2 == 0; }
+
 // NT is the LARGEST block the kernel may be launched with; the host picks blockDim.x = 32 * (warps per CTA) <= NT so
 // that every SM gets the same number of warps (see launch_eval_const in sctl_cuda.cu).
 template <class Real, int KID, int T, int NT, int RSQ, int U, int MINB>
@@ -118,20 +163,39 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
       unmasked = ((w >> (blockIdx.x & 31)) & 1u) == 0;
     }
   }
-  if (unmasked) {
-#pragma unroll U
-    for (int s = 0; s < n; s++) {
-      const Real* rec = src + s * REC;  // uniform address: LDCU into uniform registers
+  if constexpr (const_packed<Real, KID, T>()) {
+    // targets 2p and 2p+1 of this thread share one packed value; same operations per target as the scalar loop
+    f32x2 xt2[T / 2][3], acc2[T / 2][K1];
+    int lo[U][T / 2] = {};
 #pragma unroll
-      for (int j = 0; j < T; j++) pair_update<KID, RSQ, false>(acc[j], xt[j], rec, a.ctx0);
+    for (int p = 0; p < T / 2; p++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) xt2[p][k] = f32x2(xt[2 * p][k], xt[2 * p + 1][k]);
+#pragma unroll
+      for (int k = 0; k < K1; k++) acc2[p][k] = f32x2(0.0f);
     }
+    if (unmasked) const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, false>(acc2, xt2, src, n, f32x2(0.0f), lo, f32x2(0.0f));
+    else const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, true>(acc2, xt2, src, n, f32x2(0.0f), lo, f32x2(0.0f));
+#pragma unroll
+    for (int p = 0; p < T / 2; p++)
+#pragma unroll
+      for (int k = 0; k < K1; k++) {
+        acc[2 * p][k] = acc2[p][k].v.x;
+        acc[2 * p + 1][k] = acc2[p][k].v.y;
+      }
   } else {
-#pragma unroll U
-    for (int s = 0; s < n; s++) {
-      const Real* rec = src + s * REC;
+    // The refinement's loop-invariant operands (pair_math.cuh, rsqrt_masked): handed in as kernel arguments so that
+    // ptxas cannot fold them back into literals.  One zero low word per unrolled pair: each then lives in the low half of
+    // the register pair its MUFU.RSQ64H writes the high half of, for the whole loop.
+    constexpr bool HOIST = ConstHoist<Real, KID>::value;
+    int lo[U][T];
 #pragma unroll
-      for (int j = 0; j < T; j++) pair_update<KID, RSQ, true>(acc[j], xt[j], rec, a.ctx0);
-    }
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < T; j++) lo[u][j] = HOIST ? a.zero : 0;
+    const Real k = HOIST ? a.rsq_k : (Real)rsq_poly_k<RSQ>();
+    if (unmasked) const_pair_loop<Real, Real, KID, T, RSQ, U, false>(acc, xt, src, n, a.ctx0, lo, k);
+    else const_pair_loop<Real, Real, KID, T, RSQ, U, true>(acc, xt, src, n, a.ctx0, lo, k);
   }
   if (gridDim.y > 1) {
     // grid.y == cluster size: rank 0 adds the other ranks' partial sums in rank order

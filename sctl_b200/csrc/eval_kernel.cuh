@@ -130,9 +130,11 @@ template <class Real, int KID, int T, int NW, int R, int RSQ, int TILE, int STAG
   static_assert(R == 1 || (size_t)NW * T * K1 * 32 * sizeof(Real) <= STAGES * STAGE_BYTES, "reduction scratch must fit in the ring");
 };
 
-// One tile of packed records against this thread's T register-resident targets.
-template <class Real, int KID, int T, int R, int RSQ, int U, bool MASK>
-__device__ __forceinline__ void consume_tile(const Real* tile, int n, int rep, Real (&acc)[T][KerTraits<KID>::K1], const Real (&xt)[T][3], Real mu) {
+// One tile of packed records against this thread's T register-resident targets.  V is the type a pair is computed in:
+// Real, or f32x2 (two targets per value; the record's scalars are broadcast operands of the packed FP32 instructions,
+// pair_math.cuh).
+template <class V, class Real, int KID, int T, int R, int RSQ, int U, bool MASK>
+__device__ __forceinline__ void consume_tile(const Real* tile, int n, int rep, V (&acc)[T][KerTraits<KID>::K1], const V (&xt)[T][3], V mu) {
   constexpr int REC = RecTraits<Real, KID>::REC;
   constexpr int W = 16 / (int)sizeof(Real);
   using Vec16 = typename std::conditional<sizeof(Real) == 8, double2, float4>::type;
@@ -212,16 +214,44 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const E
   }
 
   const bool unmasked = a.must_mask != nullptr && a.must_mask[0] == 0;  // same value in every thread of the grid
+  // FP32 without a transcendental part: targets 2p and 2p+1 of this thread share one packed value (same operations per
+  // target as the scalar loop, hence the same bits)
+  constexpr bool PACKED = SCTL_CUDA_F32X2 && sizeof(Real) == 4 && !KerNeedsCtx<KID>::value && T % 2 == 0;
+  constexpr int TP = PACKED ? T / 2 : 1;
+  f32x2 xt2[TP][3], acc2[TP][K1];
+  if constexpr (PACKED) {
+#pragma unroll
+    for (int p = 0; p < TP; p++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) xt2[p][k] = f32x2(xt[2 * p][k], xt[2 * p + 1][k]);
+#pragma unroll
+      for (int k = 0; k < K1; k++) acc2[p][k] = f32x2(0.0f);
+    }
+  }
   for (int i = 0; i < n_tiles; i++) {
     const int st = i % STAGES;
     mbar_wait(&full[st], (i / STAGES) & 1);
     const Real* tile = ring + st * Cfg::STAGE_REALS;
     const int64_t rem = n_src - (int64_t)i * TILE;
     const int n = (int)(rem < TILE ? rem : TILE);
-    if (unmasked) consume_tile<Real, KID, T, R, RSQ, U, false>(tile, n, rep, acc, xt, a.ctx0);
-    else consume_tile<Real, KID, T, R, RSQ, U, true>(tile, n, rep, acc, xt, a.ctx0);
+    if constexpr (PACKED) {
+      if (unmasked) consume_tile<f32x2, Real, KID, TP, R, RSQ, U, false>(tile, n, rep, acc2, xt2, f32x2(0.0f));
+      else consume_tile<f32x2, Real, KID, TP, R, RSQ, U, true>(tile, n, rep, acc2, xt2, f32x2(0.0f));
+    } else {
+      if (unmasked) consume_tile<Real, Real, KID, T, R, RSQ, U, false>(tile, n, rep, acc, xt, a.ctx0);
+      else consume_tile<Real, Real, KID, T, R, RSQ, U, true>(tile, n, rep, acc, xt, a.ctx0);
+    }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
+  }
+  if constexpr (PACKED) {
+#pragma unroll
+    for (int p = 0; p < TP; p++)
+#pragma unroll
+      for (int k = 0; k < K1; k++) {
+        acc[2 * p][k] = acc2[p][k].v.x;
+        acc[2 * p + 1][k] = acc2[p][k].v.y;
+      }
   }
 
   if (R > 1) {

@@ -12,6 +12,12 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// 1: FP32 pair loops run on packed values (f32x2 below: two targets per 64-bit register pair); 0: scalar loops
+// (tools/ab_build.sh builds both to measure the difference)
+#ifndef SCTL_CUDA_F32X2
+#define SCTL_CUDA_F32X2 1
+#endif
+
 namespace sctl_cuda {
 
 // 0-4: the north-star kernels.  5-11: the other non-Helmholtz kernels of kernel_functions.hpp.
@@ -26,6 +32,34 @@ template <int KID> struct KerNeedsCtx { static constexpr bool value = (KID >= HE
 
 // How far the seed is refined; chosen on the host from `digits` (see rsq_mode_for_digits()).
 enum : int { RSQ_SEED = 0, RSQ_NEWTON = 1, RSQ_CUBIC = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// Two FP32 values in one 64-bit register pair (FP32 pair loops, two targets per value)
+// ------------------------------------------------------------------------------------------------
+// sm_100a has packed FP32 instructions, FADD2 / FMUL2 / FFMA2: one issue slot, two IEEE operations, each half rounded
+// exactly like the scalar instruction, so a loop written on f32x2 gives the same bits as the scalar loop.  The FP32
+// pair loops are issue-bound (one FFMA per cycle per SM sub-partition leaves no slot for the loads, MUFU and loop
+// control), and the packed form halves the FP32 issue count.  What makes it usable here: a packed instruction takes a
+// SCALAR 32-bit operand broadcast to both halves (SASS `FFMA2 R4, R6.F32x2.HI_LO, UR9.F32, R4.F32x2.HI_LO`, also
+// `R9.F32`), so one source value -- from a uniform register on the constant-bank path, from an LDS result on the ring
+// path -- serves the two targets of a value without being duplicated (ptxas folds f32x2(s) below into that operand).
+// The pair bodies (PairApply) are written once on `Real` and instantiate for float, double and f32x2.
+struct f32x2 {
+  float2 v;
+  __device__ __forceinline__ f32x2() {}
+  __device__ __forceinline__ f32x2(float s) : v(make_float2(s, s)) {}  // broadcast (implicit: source values, literals)
+  __device__ __forceinline__ f32x2(float lo, float hi) : v(make_float2(lo, hi)) {}
+  __device__ __forceinline__ explicit f32x2(float2 p) : v(p) {}
+};
+__device__ __forceinline__ f32x2 operator-(f32x2 a) { return f32x2(-a.v.x, -a.v.y); }
+__device__ __forceinline__ f32x2 operator+(f32x2 a, f32x2 b) { return f32x2(__fadd2_rn(a.v, b.v)); }
+__device__ __forceinline__ f32x2 operator-(f32x2 a, f32x2 b) { return f32x2(__fadd2_rn(a.v, (-b).v)); }
+__device__ __forceinline__ f32x2 operator*(f32x2 a, f32x2 b) { return f32x2(__fmul2_rn(a.v, b.v)); }
+using ::fma;  // the overload below must not hide fma(double, double, double) / fma(float, float, float) in this namespace
+__device__ __forceinline__ f32x2 fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2(__ffma2_rn(a.v, b.v, c.v)); }
+__device__ __forceinline__ f32x2& operator+=(f32x2& a, f32x2 b) { return a = a + b; }
+__device__ __forceinline__ f32x2& operator-=(f32x2& a, f32x2 b) { return a = a - b; }
+__device__ __forceinline__ f32x2& operator*=(f32x2& a, f32x2 b) { return a = a * b; }
 
 // ------------------------------------------------------------------------------------------------
 // Masked reciprocal square root:  r2 > 0 ? r2^(-1/2) : 0     (approx_rsqrt<digits>(r2, r2 > 0))
@@ -50,7 +84,15 @@ constexpr double RSQ_NEWTON_A = 1.0 + 0.375 * (2.3e-13 - 2.65e-7 * 2.65e-7);
 // MASK = false drops the compare + select.  It is bit-identical to MASK = true whenever r2 >= 2^-1022 (or NaN/Inf),
 // and the host only selects it after coincidence_probe_kernel has shown that no (source, target) pair can have a
 // smaller r2 (eval_kernel.cuh); the two instructions cost ~3 % of the Stokes pair (profiles/r1_whatif.txt).
-template <int MODE, bool MASK = true> __device__ __forceinline__ double rsqrt_masked(double x) {
+// `lo` and `k` are the two loop-invariant operands of the refinement: the seed's low word (always 0: MUFU.RSQ64H only
+// writes the high word) and the polynomial coefficient that cannot be an immediate because the same DFMA already
+// carries one (3/8 for RSQ_CUBIC, B for RSQ_NEWTON).  Given as literals (the one-argument overload below) ptxas
+// re-materialises both inside the pair loop: one IMAD.MOV per pair for the low word, two per iteration for the
+// coefficient.  A pair loop that hands in values ptxas cannot fold (kernel arguments: eval_const_kernel.cuh) keeps the
+// coefficient in one register pair and lets MUFU.RSQ64H write the high half of a pair whose low half stays zero, so
+// none of those moves is left in the loop.  The arithmetic, and so every result bit, is the same.
+template <int MODE> __host__ __device__ constexpr double rsq_poly_k() { return MODE == RSQ_NEWTON ? RSQ_NEWTON_B : 0.375; }
+template <int MODE, bool MASK = true> __device__ __forceinline__ double rsqrt_masked(double x, int lo, double k) {
   // One signed compare on the high word: false for zero, subnormal and negative inputs, then a select on the seed's high
   // word; its low word is zero anyway.  NaN / Inf inputs are NOT masked and propagate as NaN.  (The reference's r2 > 0
   // compare is false for NaN, so there a NaN pair is dropped by kernels that only multiply by rinv, e.g. Laplace3D_FxU,
@@ -60,25 +102,37 @@ template <int MODE, bool MASK = true> __device__ __forceinline__ double rsqrt_ma
   // (tools/probe.cu, probe4), so the mask is kept to compare + select.
   double ys;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(ys) : "d"(x));
-  const double y0 = MASK ? __hiloint2double(__double2hiint(x) >= 0x00100000 ? __double2hiint(ys) : 0, 0) : ys;
+  const int hs = __double2hiint(ys);
+  const double y0 = __hiloint2double(MASK ? (__double2hiint(x) >= 0x00100000 ? hs : 0) : hs, lo);
   if (MODE == RSQ_SEED) return y0;
   const double e = fma(-x, y0 * y0, 1.0);
   // Written as y0 * (1 + e*p) rather than y0 + (y0*e)*p: every instruction then reads at most two distinct
   // vector registers.  A DFMA with three distinct register sources issues every 3 cycles instead of 2 on B200.
-  if (MODE == RSQ_NEWTON) return y0 * fma(e, RSQ_NEWTON_B, RSQ_NEWTON_A);
-  return y0 * fma(e, fma(e, 0.375, 0.5), 1.0);
+  if (MODE == RSQ_NEWTON) return y0 * fma(e, k, RSQ_NEWTON_A);
+  return y0 * fma(e, fma(e, k, 0.5), 1.0);
+}
+template <int MODE, bool MASK = true> __device__ __forceinline__ double rsqrt_masked(double x) {
+  return rsqrt_masked<MODE, MASK>(x, 0, rsq_poly_k<MODE>());
 }
 
 // FP32.  Seed = MUFU.RSQ (2^-22 relative error): that already meets approx_rsqrt<digits<=6>, which is what the
 // reference computes for float by default (digits = (int)(23*0.30103) = 6, vec.txx:376).  digits >= 7 adds one
 // Newton step on the FP32 pipe.  Same masking rule as FP64 (subnormal r2 means |dx| < 1.1e-19).
-template <int MODE, bool MASK = true> __device__ __forceinline__ float rsqrt_masked(float x) {
+template <int MODE, bool MASK = true> __device__ __forceinline__ float rsqrt_masked(float x, int = 0, float = 0) {
   float ys;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(ys) : "f"(x));
   const float y0 = MASK ? (__float_as_int(x) >= 0x00800000 ? ys : 0.0f) : ys;
   if (MODE == RSQ_SEED) return y0;
   const float e = fmaf(-x, y0 * y0, 1.0f);
   return y0 * fmaf(e, 0.5f, 1.0f);
+}
+// Two FP32 values: one MUFU.RSQ (and one compare + select) per half, the Newton step packed.  Same operations per half as
+// the float overload, hence the same bits.
+template <int MODE, bool MASK = true> __device__ __forceinline__ f32x2 rsqrt_masked(f32x2 x, int = 0, f32x2 = f32x2()) {
+  const f32x2 y0(rsqrt_masked<RSQ_SEED, MASK>(x.v.x), rsqrt_masked<RSQ_SEED, MASK>(x.v.y));
+  if (MODE == RSQ_SEED) return y0;
+  const f32x2 e = fma(-x, y0 * y0, f32x2(1.0f));
+  return y0 * fma(e, f32x2(0.5f), f32x2(1.0f));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -158,13 +212,13 @@ template <int KID, class Real> struct PairApply;
 
 // u = rinv                                   (kernel_functions.hpp:43-47)
 template <class Real> struct PairApply<LAPLACE3D_FXU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[1], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[1], const Real (&dx)[3], Real rinv, const S* s) {
     acc[0] = fma(rinv, s[3], acc[0]);
   }
 };
 // u = (r.n) rinv^3; the record carries g = f*n so the pair costs one dot product      (:72-78)
 template <class Real> struct PairApply<LAPLACE3D_DXU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[1], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[1], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv3 = rinv * rinv * rinv;
     const Real d = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3]));
     acc[0] = fma(d, rinv3, acc[0]);
@@ -172,7 +226,7 @@ template <class Real> struct PairApply<LAPLACE3D_DXU, Real> {
 };
 // v_i += r_i (f rinv^3)                      (fused apply, :102-110)
 template <class Real> struct PairApply<LAPLACE3D_FXDU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const S* s) {
     const Real t = (rinv * rinv) * (rinv * s[3]);
     acc[0] = fma(dx[0], t, acc[0]);
     acc[1] = fma(dx[1], t, acc[1]);
@@ -181,7 +235,7 @@ template <class Real> struct PairApply<LAPLACE3D_FXDU, Real> {
 };
 // v_i += f_i rinv + r_i (f.r) rinv^3  =  rinv (f_i + r_i (f.r) rinv^2)      (fused apply, :166-176)
 template <class Real> struct PairApply<STOKES3D_FXU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     const Real d = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3]));
     const Real c = d * rinv2;
@@ -192,7 +246,7 @@ template <class Real> struct PairApply<STOKES3D_FXU, Real> {
 };
 // v_i += r_i (f.r)(r.n) rinv^5              (fused apply, :205-217)
 template <class Real> struct PairApply<STOKES3D_DXU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     const Real rinv5 = (rinv2 * rinv2) * rinv;
     const Real df = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3]));
@@ -208,7 +262,7 @@ template <class Real> struct PairApply<STOKES3D_DXU, Real> {
 // ---- the other non-Helmholtz kernels (kernel_functions.hpp:220-483) ----
 // Stokes3D_FxT: v_ij += r_i r_j (f.r) rinv^5                    (fused apply, :241-252)
 template <class Real> struct PairApply<STOKES3D_FXT, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     const Real rinv5 = (rinv2 * rinv2) * rinv;
     const Real t = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) * rinv5;
@@ -222,7 +276,7 @@ template <class Real> struct PairApply<STOKES3D_FXT, Real> {
 };
 // Stokes3D_FSxU: v_i += f_i rinv + r_i (f.r + f_3) rinv^3        (fused apply, :311-321)
 template <class Real> struct PairApply<STOKES3D_FSXU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     // one source value per instruction: a DFMA can take a single uniform-register operand (constant-bank path)
     const Real c = (fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) + s[6]) * rinv2;
@@ -233,7 +287,7 @@ template <class Real> struct PairApply<STOKES3D_FSXU, Real> {
 };
 // Stokes3D_FxUP: velocity as Stokes3D_FxU, pressure v_3 += (f.r) rinv^3   (fused apply, :351-362)
 template <class Real> struct PairApply<STOKES3D_FXUP, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[4], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[4], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     const Real c = fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) * rinv2;
     acc[0] = fma(rinv, fma(dx[0], c, s[3]), acc[0]);
@@ -244,7 +298,7 @@ template <class Real> struct PairApply<STOKES3D_FXUP, Real> {
 };
 // Laplace3D_Fxd2U: v_ij += f (3 r_i r_j rinv^5 - delta_ij rinv^3)        (uKerMatrix + FMA, :376-388)
 template <class Real> struct PairApply<LAPLACE3D_FXD2U, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     const Real g = (rinv2 * rinv) * s[3];
     const Real h = (g * rinv2) * (Real)3;
@@ -259,7 +313,7 @@ template <class Real> struct PairApply<LAPLACE3D_FXD2U, Real> {
 };
 // Laplace3D_DxdU: v_i += f (n_i rinv^3 - 3 r_i (r.n) rinv^5); the record carries g = f*n     (:402-411)
 template <class Real> struct PairApply<LAPLACE3D_DXDU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     const Real rinv3 = rinv2 * rinv;
     const Real c = (fma(dx[2], s[5], fma(dx[1], s[4], dx[0] * s[3])) * rinv2) * (Real)3;
@@ -270,7 +324,7 @@ template <class Real> struct PairApply<LAPLACE3D_DXDU, Real> {
 };
 // BiotSavart3D_FxU: v += (f x r) rinv^3                                  (fused apply, :436-447)
 template <class Real> struct PairApply<BIOTSAVART3D_FXU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[3], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv3 = rinv * rinv * rinv;
     acc[0] = fma(fma(s[4], dx[2], -(dx[1] * s[5])), rinv3, acc[0]);
     acc[1] = fma(fma(s[5], dx[0], -(dx[2] * s[3])), rinv3, acc[1]);
@@ -280,7 +334,7 @@ template <class Real> struct PairApply<BIOTSAVART3D_FXU, Real> {
 // BiotSavart3D_FxdU: v_ab += eps_abk f_k rinv^3 + 3 (f x r)_a r_b rinv^5   (uKerMatrix + FMA, :460-482; the 3 x 9
 // block is the negated gradient of the FxU block, its sign lives in the scale factor)
 template <class Real> struct PairApply<BIOTSAVART3D_FXDU, Real> {
-  static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const Real* s) {
+  template <class S> static __device__ __forceinline__ void run(Real (&acc)[9], const Real (&dx)[3], Real rinv, const S* s) {
     const Real rinv2 = rinv * rinv;
     const Real rinv3 = rinv2 * rinv;
     const Real t5 = (rinv3 * rinv2) * (Real)3;
@@ -432,14 +486,19 @@ template <class Real> struct PairApply<HELMHOLTZDIFF3D_FXDU, Real> {  // uKerMat
 
 // One source-target pair, starting from coordinates.
 // `mu` is the kernel context (the Helmholtz wavenumber); the other kernels ignore it.
-template <int KID, int RSQ, bool MASK = true, class Real>
-__device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], const Real (&xt)[3], const Real* s, Real mu = 0) {
+// `lo`, `k`: the refinement's loop-invariant operands (rsqrt_masked above); callers that do not hoist them leave the
+// defaults, which are the literals.
+// Real is the type the pair is computed in (double, float, or f32x2 = two targets at once); S the scalar type of the
+// record (Real itself, or float for f32x2).
+template <int KID, int RSQ, bool MASK = true, class Real, class S>
+__device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], const Real (&xt)[3], const S* s, Real mu = Real(0), int lo = 0,
+                                            Real k = Real((S)rsq_poly_k<RSQ>())) {
   Real dx[3];
   dx[0] = xt[0] - s[0];
   dx[1] = xt[1] - s[1];
   dx[2] = xt[2] - s[2];
   const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
-  const Real rinv = rsqrt_masked<RSQ, MASK>(r2);
+  const Real rinv = rsqrt_masked<RSQ, MASK>(r2, lo, k);
   if constexpr (KerNeedsCtx<KID>::value) PairApply<KID, Real>::run_ctx(acc, dx, rinv, s, r2, mu);
   else PairApply<KID, Real>::run(acc, dx, rinv, s);
 }

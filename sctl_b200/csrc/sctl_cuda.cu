@@ -131,8 +131,9 @@ struct Options {
   int64_t const_ctas_per_sm = 6;
   int64_t const_ctas_per_sm_overlap = 1;
   // FP32 on the constant-bank path: 0 never, 1 always (above const_min_targets), -1 (default) where it measured faster
-  // than the shared-memory ring (profiles/r1_fp32_paths.md): Nt >= 2^17 and every kernel but Laplace3D_FxU, with
-  // const_banks_fp32 slices in flight (FP32 launches are half as long, so four slices hide their boundaries better)
+  // than the shared-memory ring with the packed FP32 loops (profiles/r2c_ab_rate32_packed_vs_scalar.md): Nt >= 2^17 for
+  // every kernel (at 2^15 the two are within a few per cent of each other either way), with const_banks_fp32 slices in
+  // flight (FP32 launches are half as long, so four slices hide their boundaries better)
   int64_t const_fp32 = -1;
   int64_t const_banks_fp32 = 4;
   // Above this many pairs Eval first runs the O(Ns+Nt) coincidence probe (coincidence.cuh) and lets the pair kernels
@@ -238,12 +239,19 @@ template <class Real> int rsq_mode_for_digits(int digits) {
 // ---------------------------------------------------------------------------------------------
 // MAIN: many targets.  FEW: few targets -- all warps of a CTA share 32*T targets and split the sources.
 // CONST: very many targets -- sources streamed through the constant bank into uniform registers (eval_const_kernel.cuh).
+// the FP64 constant-bank shape can be overridden at build time for tuning runs (tools/ab_build.sh)
+#ifndef SCTL_TUNE_CONST_NT
+#define SCTL_TUNE_CONST_NT 256
+#endif
+#ifndef SCTL_TUNE_CONST_U
+#define SCTL_TUNE_CONST_U 4
+#endif
 template <class Real> struct Tune;
 template <> struct Tune<double> {
   static constexpr int T = 2, NW = 8, TILE = 256, STAGES = 3, MINB = 2;
   static constexpr int WIDE_T = 4, WIDE_NW = 8, WIDE_TILE = 256, WIDE_STAGES = 3, WIDE_MINB = 1;
   static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 256, FEW_STAGES = 3, FEW_MINB = 2;
-  static constexpr int CONST_T = 2, CONST_NT = 256, CONST_U = 4, CONST_MINB = 2;
+  static constexpr int CONST_T = 2, CONST_NT = SCTL_TUNE_CONST_NT, CONST_U = SCTL_TUNE_CONST_U, CONST_MINB = 2;
 };
 template <> struct Tune<float> {
   static constexpr int T = 4, NW = 8, TILE = 512, STAGES = 3, MINB = 2;
@@ -365,6 +373,8 @@ int launch_eval_const(int dev, const ConstGeom& cg, bool use_bits, int64_t Ns, i
   a.allow_unmasked = flags != nullptr;
   a.ctx0 = ctx0;
   a.scale = scale_factor<Real>(KID);
+  a.zero = 0;
+  a.rsq_k = (Real)rsq_poly_k<RSQ>();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)n_tb, (unsigned)cl);
   cfg.blockDim = dim3(NT);
@@ -461,7 +471,7 @@ template <class Real, int KID, int RSQ>
 int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, Real ctx0, cudaStream_t stream) {
   using Tn = Tune<Real>;
   constexpr int REC = RecTraits<Real, KID>::REC;
-  const bool fp32_const = g.opt.const_fp32 == 1 || (g.opt.const_fp32 < 0 && Nt >= (1 << 17) && KID != LAPLACE3D_FXU);
+  const bool fp32_const = g.opt.const_fp32 == 1 || (g.opt.const_fp32 < 0 && Nt >= (1 << 17));
   const bool use_const = Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || fp32_const);
   // coincidence probe (big problems only): lets the pair kernels skip the r2 == 0 mask where it cannot matter
   const bool probe = g.opt.probe_min_pairs > 0 && (double)Ns * (double)Nt >= (double)g.opt.probe_min_pairs;

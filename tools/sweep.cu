@@ -199,6 +199,7 @@ void run_const(Ctx& c, int n_sub = 1, int wpc = 0) {
   a.v_trg = (Real*)c.v_trg;
   a.Nt = c.Nt;
   a.scale = scale_factor<Real>(KID);
+  a.rsq_k = (Real)rsq_poly_k<RSQ>();
   const int tpb = 32 * wpc * T;
   dim3 grid((unsigned)((c.Nt + tpb - 1) / tpb), (unsigned)n_sub);
   cudaLaunchConfig_t cfg = {};
@@ -261,6 +262,7 @@ void run_const_breakdown(Ctx& c) {
   a.v_trg = (Real*)c.v_trg;
   a.Nt = c.Nt;
   a.scale = scale_factor<Real>(KID);
+  a.rsq_k = (Real)rsq_poly_k<RSQ>();
   a.n_rec = CH;
   a.sub_len = CH;
   a.full_ranks = 1;
