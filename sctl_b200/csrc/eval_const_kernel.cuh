@@ -125,8 +125,8 @@ __device__ __forceinline__ void const_pair_loop(V (&acc)[T][KerTraits<KID>::K1],
   }
 }
 
-// FP32 pair loops run on packed values (two targets each) where the kernel has no transcendental part
-template <class Real, int KID, int T> __host__ __device__ constexpr bool const_packed() { return SCTL_CUDA_F32X2 && sizeof(Real) == 4 && !KerNeedsCtx<KID>::value && T % 2 == 0; }
+// FP32 pair loops run on packed values (two targets each)
+template <class Real, int KID, int T> __host__ __device__ constexpr bool const_packed() { return SCTL_CUDA_F32X2 && sizeof(Real) == 4 && T % 2 == 0; }
 
 // NT is the LARGEST block the kernel may be launched with; the host picks blockDim.x = 32 * (warps per CTA) <= NT so
 // that every SM gets the same number of warps (see launch_eval_const in sctl_cuda.cu).
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
 #pragma unroll
       for (int k = 0; k < K1; k++) acc2[p][k] = f32x2(0.0f);
     }
-    if (unmasked) const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, false>(acc2, xt2, src, n, f32x2(0.0f), lo, f32x2(0.0f));
-    else const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, true>(acc2, xt2, src, n, f32x2(0.0f), lo, f32x2(0.0f));
+    if (unmasked) const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, false>(acc2, xt2, src, n, f32x2((float)a.ctx0), lo, f32x2(0.0f));
+    else const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, true>(acc2, xt2, src, n, f32x2((float)a.ctx0), lo, f32x2(0.0f));
 #pragma unroll
     for (int p = 0; p < T / 2; p++)
 #pragma unroll

@@ -214,9 +214,9 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const E
   }
 
   const bool unmasked = a.must_mask != nullptr && a.must_mask[0] == 0;  // same value in every thread of the grid
-  // FP32 without a transcendental part: targets 2p and 2p+1 of this thread share one packed value (same operations per
-  // target as the scalar loop, hence the same bits)
-  constexpr bool PACKED = SCTL_CUDA_F32X2 && sizeof(Real) == 4 && !KerNeedsCtx<KID>::value && T % 2 == 0;
+  // FP32: targets 2p and 2p+1 of this thread share one packed value (same operations per target as the scalar loop,
+  // hence the same bits)
+  constexpr bool PACKED = SCTL_CUDA_F32X2 && sizeof(Real) == 4 && T % 2 == 0;
   constexpr int TP = PACKED ? T / 2 : 1;
   f32x2 xt2[TP][3], acc2[TP][K1];
   if constexpr (PACKED) {
@@ -235,8 +235,8 @@ __global__ void __launch_bounds__((NW + 1) * 32, MINB) eval_pairs_kernel(const E
     const int64_t rem = n_src - (int64_t)i * TILE;
     const int n = (int)(rem < TILE ? rem : TILE);
     if constexpr (PACKED) {
-      if (unmasked) consume_tile<f32x2, Real, KID, TP, R, RSQ, U, false>(tile, n, rep, acc2, xt2, f32x2(0.0f));
-      else consume_tile<f32x2, Real, KID, TP, R, RSQ, U, true>(tile, n, rep, acc2, xt2, f32x2(0.0f));
+      if (unmasked) consume_tile<f32x2, Real, KID, TP, R, RSQ, U, false>(tile, n, rep, acc2, xt2, f32x2((float)a.ctx0));
+      else consume_tile<f32x2, Real, KID, TP, R, RSQ, U, true>(tile, n, rep, acc2, xt2, f32x2((float)a.ctx0));
     } else {
       if (unmasked) consume_tile<Real, Real, KID, T, R, RSQ, U, false>(tile, n, rep, acc, xt, a.ctx0);
       else consume_tile<Real, Real, KID, T, R, RSQ, U, true>(tile, n, rep, acc, xt, a.ctx0);

@@ -424,6 +424,34 @@ __device__ __forceinline__ void sincos_real(float x, float* s, float* c) {
   *c = __int_as_float(__float_as_int(c0) ^ (((q + 1) & 2) << 30));
 }
 
+// Two FP32 arguments at once: the reduction and the polynomials run on the packed FP32 instructions, the quadrant fix-up
+// per half on the integer pipe.  Same operations per half as the float version (same bits); a value with either half out
+// of range takes the scalar path for both.
+__device__ __forceinline__ void sincos_real(f32x2 x, f32x2* s, f32x2* c) {
+  if (!(fabsf(x.v.x) <= 4.5e4f && fabsf(x.v.y) <= 4.5e4f)) {
+    sincos_real(x.v.x, &s->v.x, &c->v.x);
+    sincos_real(x.v.y, &s->v.y, &c->v.y);
+    return;
+  }
+  const f32x2 t = fma(x, f32x2(0.636619772367581f), f32x2(12582912.0f));
+  const f32x2 n = t - f32x2(12582912.0f);
+  f32x2 r = fma(n, f32x2(-1.57079637050628662109375f), x);
+  r = fma(n, f32x2(4.37113882867379237e-8f), r);
+  r = fma(n, f32x2(1.71512451e-15f), r);
+  const f32x2 z = r * r;
+  f32x2 ps = fma(z, f32x2(-1.9515295891e-4f), f32x2(8.3321608736e-3f));
+  f32x2 pc = fma(z, f32x2(2.443315711809948e-5f), f32x2(-1.388731625493765e-3f));
+  ps = fma(z, ps, f32x2(-1.6666654611e-1f));
+  pc = fma(z, pc, f32x2(4.166664568298827e-2f));
+  const f32x2 sr = fma(r * z, ps, r);
+  const f32x2 cr = fma(z, fma(z, pc, f32x2(-0.5f)), f32x2(1.0f));
+  const int q0 = __float_as_int(t.v.x), q1 = __float_as_int(t.v.y);
+  const float s0 = (q0 & 1) ? cr.v.x : sr.v.x, c0 = (q0 & 1) ? sr.v.x : cr.v.x;
+  const float s1 = (q1 & 1) ? cr.v.y : sr.v.y, c1 = (q1 & 1) ? sr.v.y : cr.v.y;
+  *s = f32x2(__int_as_float(__float_as_int(s0) ^ ((q0 & 2) << 30)), __int_as_float(__float_as_int(s1) ^ ((q1 & 2) << 30)));
+  *c = f32x2(__int_as_float(__float_as_int(c0) ^ (((q0 + 1) & 2) << 30)), __int_as_float(__float_as_int(c1) ^ (((q1 + 1) & 2) << 30)));
+}
+
 // (G0, G1) of the gradient-type kernels: (-mu sin - cos/r, mu cos - sin/r) / r^2;  DIFF subtracts the Laplace part
 // through the half-angle identity cos(x) - 1 = -2 sin^2(x/2) (:640-647)
 template <bool DIFF, class Real> __device__ __forceinline__ void helmholtz_grad_G(Real& G0, Real& G1, Real r2, Real rinv, Real mu) {
@@ -443,7 +471,7 @@ template <bool DIFF, class Real> __device__ __forceinline__ void helmholtz_grad_
   G1 = (mu * cs - sn * rinv) * rinv2;
 }
 template <class Real> struct PairApply<HELMHOLTZ3D_FXU, Real> {  // :519-532
-  static __device__ __forceinline__ void run_ctx(Real (&acc)[2], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+  template <class S> static __device__ __forceinline__ void run_ctx(Real (&acc)[2], const Real (&dx)[3], Real rinv, const S* s, Real r2, Real mu) {
     Real sn, cs;
     sincos_real((r2 * rinv) * mu, &sn, &cs);
     const Real G0 = cs * rinv, G1 = sn * rinv;
@@ -452,7 +480,7 @@ template <class Real> struct PairApply<HELMHOLTZ3D_FXU, Real> {  // :519-532
   }
 };
 template <class Real> struct PairApply<HELMHOLTZ3D_DXU, Real> {  // :561-577
-  static __device__ __forceinline__ void run_ctx(Real (&acc)[2], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+  template <class S> static __device__ __forceinline__ void run_ctx(Real (&acc)[2], const Real (&dx)[3], Real rinv, const S* s, Real r2, Real mu) {
     Real G0, G1;
     helmholtz_grad_G<false>(G0, G1, r2, rinv, mu);
     const Real ndotr = fma(dx[2], s[7], fma(dx[1], s[6], dx[0] * s[5]));
@@ -462,7 +490,7 @@ template <class Real> struct PairApply<HELMHOLTZ3D_DXU, Real> {  // :561-577
     acc[1] = fma(s[3], G1, fma(s[4], G0, acc[1]));
   }
 };
-template <bool DIFF, class Real> __device__ __forceinline__ void helmholtz_fxdu_apply(Real (&acc)[6], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+template <bool DIFF, class Real, class S> __device__ __forceinline__ void helmholtz_fxdu_apply(Real (&acc)[6], const Real (&dx)[3], Real rinv, const S* s, Real r2, Real mu) {
   Real G0, G1;
   helmholtz_grad_G<DIFF>(G0, G1, r2, rinv, mu);
   const Real fG0 = fma(s[3], G0, -(s[4] * G1));
@@ -474,12 +502,12 @@ template <bool DIFF, class Real> __device__ __forceinline__ void helmholtz_fxdu_
   }
 }
 template <class Real> struct PairApply<HELMHOLTZ3D_FXDU, Real> {  // :607-626
-  static __device__ __forceinline__ void run_ctx(Real (&acc)[6], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+  template <class S> static __device__ __forceinline__ void run_ctx(Real (&acc)[6], const Real (&dx)[3], Real rinv, const S* s, Real r2, Real mu) {
     helmholtz_fxdu_apply<false>(acc, dx, rinv, s, r2, mu);
   }
 };
 template <class Real> struct PairApply<HELMHOLTZDIFF3D_FXDU, Real> {  // uKerMatrix + FMA, :629-657
-  static __device__ __forceinline__ void run_ctx(Real (&acc)[6], const Real (&dx)[3], Real rinv, const Real* s, Real r2, Real mu) {
+  template <class S> static __device__ __forceinline__ void run_ctx(Real (&acc)[6], const Real (&dx)[3], Real rinv, const S* s, Real r2, Real mu) {
     helmholtz_fxdu_apply<true>(acc, dx, rinv, s, r2, mu);
   }
 };

@@ -147,7 +147,8 @@ def test_cpp_host_layer_compiles_standalone(tmp_path):
 def test_sass_evidence_of_the_b200_design(sbm):
     """cuobjdump of the shipped library: the shared-memory kernels stream sources with TMA bulk copies (UBLKCP) behind
     mbarriers (SYNCS), seed the reciprocal square root with MUFU.RSQ64H, and the constant-bank kernels feed FP64
-    instructions with uniform-register operands loaded by LDCU (no vector LDC of the source records)."""
+    instructions with uniform-register operands loaded by LDCU (no vector LDC of the source records), and the FP32 pair loops
+    use the packed FP32 instructions with broadcast scalar operands."""
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
@@ -168,7 +169,14 @@ def test_sass_evidence_of_the_b200_design(sbm):
         # and this CTA's coincidence-bit word), never the source records inside the loops
         # (the Helmholtz kernels also load sincos polynomial coefficients from the bank: exempt)
         assert id(body) in helmholtz or len(re.findall(r" LDC(\.\d+)? R\d+, c\[0x3\]", body)) <= 2
-        assert len(re.findall(r"[DF](FMA|MUL|ADD) [^;]*UR\d+", body)) >= 40
+        assert len(re.findall(r"[DF](FMA|MUL|ADD)2? [^;]*UR\d+", body)) >= 40
+    # FP32 pair loops are packed (two targets per 64-bit register pair): FFMA2 / FMUL2 / FADD2 with the source value as a
+    # broadcast scalar operand -- a uniform register on the constant-bank path, an LDS result on the ring path
+    for n, body in funcs.items():
+        if re.search(r"eval_pairs_const_kernelIfLi\d+ELi4E", n):
+            assert len(re.findall(r"F(FMA|MUL|ADD)2 [^;]*UR\d+\.F32", body)) >= 10, n
+        if re.search(r"eval_pairs_kernelIfLi\d+ELi4E", n):  # T = 4 (main / wide); the few-target variant has T = 1
+            assert len(re.findall(r"F(FMA|MUL|ADD)2 [^;]* -?R\d+\.F32", body)) >= 10, n
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", sbm.LIB_PATH], capture_output=True, text=True).stdout
 
 
