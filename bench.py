@@ -35,6 +35,9 @@ UNIT = "pairs/s"
 F_ALG = {"Laplace3D_FxU": 11, "Laplace3D_DxU": 19, "Laplace3D_FxdU": 18, "Stokes3D_FxU": 29, "Stokes3D_DxU": 30}
 SCTL_FLOPS = {"Laplace3D_FxU": 6, "Laplace3D_DxU": 14, "Laplace3D_FxdU": 11, "Stokes3D_FxU": 23, "Stokes3D_DxU": 26}  # uKernel::FLOPS()
 FP_INSTR = {"Laplace3D_FxU": 12, "Laplace3D_DxU": 17, "Laplace3D_FxdU": 17, "Stokes3D_FxU": 22, "Stokes3D_DxU": 25}  # FP-pipe instructions per pair (f64)
+# FP32 at digits -1: the MUFU.RSQ seed alone (XU pipe), so the 5 refinement instructions go; packed two pairs per instruction,
+# which halves the issue slots but not the pipe cycles
+FP_INSTR32 = {k: v - 5 for k, v in FP_INSTR.items()}
 DIMS = {"Laplace3D_FxU": (1, 1, 0), "Laplace3D_DxU": (1, 1, 3), "Laplace3D_FxdU": (1, 3, 0), "Stokes3D_FxU": (3, 3, 0), "Stokes3D_DxU": (3, 3, 3)}
 
 
@@ -319,15 +322,21 @@ def main():
     const_path = plan["n_launches"] > 10  # one launch per source chunk (the ring paths need at most 5)
     # launches of one Eval on the constant-bank path: pack + 2 probe kernels + one pair kernel per chunk + the bank combine
     pair_launches = max(1, plan["n_launches"] - 4) if const_path else 1
+    # FP-pipe instructions per pair of the loop that ran: FP64 by digits class (cubic / first-order / seed only), FP32 seed
+    # only at digits -1 .. 6 and one Newton step (3 instructions) above
+    if rb == 8:
+        fp_instr = FP_INSTR[kernel] - (0 if (args.digits < 0 or args.digits >= 12) else 1 if args.digits >= 6 else 5)
+    else:
+        fp_instr = FP_INSTR32[kernel] + (3 if args.digits >= 7 else 0)
     roofline = {"bound": "fp64" if rb == 8 else "fp32", "achieved": achieved, "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained, "traffic": traffic,
                 "peak_source": "%s micro-benchmark in this run (sctl_cuda_fma_peak, 1.5 s sustained, FMA = 2 flop); burst 50 ms figure %.2f; MEASURED_PEAKS.json has no FP64/FP32 CUDA-core entry" % ("DFMA" if rb == 8 else "FFMA", peak_burst),
-                "note": "compute-bound on the FP64 CUDA-core pipe (pointwise rsqrt/FMA, ~0 bytes per pair): neither 'hbm' nor 'tensor' applies",
+                "note": "compute-bound on the %s CUDA-core pipe (pointwise rsqrt/FMA, ~0 bytes per pair): neither 'hbm' nor 'tensor' applies" % ("FP64" if rb == 8 else "FP32"),
                 "kernel": "eval_pairs%s_kernel<%s, %s>" % ("_const" if const_path else "", "double" if rb == 8 else "float", kernel),
                 "kernel_ms_per_step": k_ms, "pair_kernel_launches_per_step": pair_launches,
-                "launch_overlap": "chunk i runs from constant-bank slice i % 2 on its own stream, so consecutive pair-kernel launches overlap; kernel_ms_per_step is the wall time of the whole chain on the device" if const_path else None,
+                "launch_overlap": "chunk i runs from constant-bank slice i %% %d on its own stream, so consecutive pair-kernel launches overlap; kernel_ms_per_step is the wall time of the whole chain on the device" % (2 if rb == 8 else 4) if const_path else None,
                 "pairs_per_step": my_pairs, "flop_per_pair": F_ALG[kernel],
                 "frac_sctl_flops_convention": my_pairs * SCTL_FLOPS[kernel] / (k_ms * 1e-3) * 1e-12 / peak_sustained,
-                "fp_instr_per_pair": FP_INSTR[kernel], "pipe_ceiling_frac": F_ALG[kernel] / (2.0 * FP_INSTR[kernel])}
+                "fp_instr_per_pair": fp_instr, "pipe_ceiling_frac": F_ALG[kernel] / (2.0 * fp_instr)}
     if traffic is not None and const_path:
         # the contract's HBM view of the same kernel, to show that it is not the binding roof: DRAM bytes of one pair-kernel
         # launch (ncu) x launches per step / kernel time, against the measured copy bandwidth

@@ -239,12 +239,24 @@ template <class Real> int rsq_mode_for_digits(int digits) {
 // ---------------------------------------------------------------------------------------------
 // MAIN: many targets.  FEW: few targets -- all warps of a CTA share 32*T targets and split the sources.
 // CONST: very many targets -- sources streamed through the constant bank into uniform registers (eval_const_kernel.cuh).
-// the FP64 constant-bank shape can be overridden at build time for tuning runs (tools/ab_build.sh)
+// the constant-bank shapes (FP64, FP32) can be overridden at build time for tuning runs (tools/ab_build.sh)
 #ifndef SCTL_TUNE_CONST_NT
 #define SCTL_TUNE_CONST_NT 256
 #endif
 #ifndef SCTL_TUNE_CONST_U
 #define SCTL_TUNE_CONST_U 4
+#endif
+#ifndef SCTL_TUNE_CONST32_T
+#define SCTL_TUNE_CONST32_T 4
+#endif
+#ifndef SCTL_TUNE_CONST32_NT
+#define SCTL_TUNE_CONST32_NT 128
+#endif
+#ifndef SCTL_TUNE_CONST32_U
+#define SCTL_TUNE_CONST32_U 4
+#endif
+#ifndef SCTL_TUNE_CONST32_MINB
+#define SCTL_TUNE_CONST32_MINB 4
 #endif
 template <class Real> struct Tune;
 template <> struct Tune<double> {
@@ -257,7 +269,7 @@ template <> struct Tune<float> {
   static constexpr int T = 4, NW = 8, TILE = 512, STAGES = 3, MINB = 2;
   static constexpr int WIDE_T = 4, WIDE_NW = 8, WIDE_TILE = 512, WIDE_STAGES = 3, WIDE_MINB = 2;
   static constexpr int FEW_T = 1, FEW_NW = 8, FEW_TILE = 512, FEW_STAGES = 3, FEW_MINB = 2;
-  static constexpr int CONST_T = 4, CONST_NT = 128, CONST_U = 2, CONST_MINB = 4;
+  static constexpr int CONST_T = SCTL_TUNE_CONST32_T, CONST_NT = SCTL_TUNE_CONST32_NT, CONST_U = SCTL_TUNE_CONST32_U, CONST_MINB = SCTL_TUNE_CONST32_MINB;
 };
 
 struct DevBuf {

@@ -8,4 +8,4 @@ name=$1; shift
 cd "$(dirname "$0")/../sctl_b200/csrc"
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -ccbin /usr/bin/g++ -Xcompiler -fPIC,-O2 \
   -Xptxas -v "$@" -shared -o ../../tools/ab_$name.so sctl_cuda.cu -lcudart -ldl 2> ../../tools/ab_$name.ptxas.txt
-grep -A2 "eval_pairs_const_kernelIdLi3ELi2E" ../../tools/ab_$name.ptxas.txt | grep -E "Used|spill" | head -6
+grep -A2 "eval_pairs_const_kernelI[df]Li3E" ../../tools/ab_$name.ptxas.txt | grep -E "Used|spill" | head -6
