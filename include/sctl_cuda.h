@@ -220,9 +220,8 @@ int sctl_cuda_bio_apply(sctl_cuda_bio_t h, int digits, const void* F, int64_t nF
 int sctl_cuda_bio_last_timing(sctl_cuda_bio_t h, double* far_ms, double* tail_ms, double* total_ms);
 
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
- *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64;
- *                       FP32 per "const_fp32": 0 never, 1 always, -1 (default) for Nt >= 2^17 and every kernel but
- *                       Laplace3D_FxU, where it measured faster than the shared-memory ring);
+ *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64,
+ *                       and FP32 unless "const_fp32" is 0, which keeps FP32 on the shared-memory ring);
  *   "wide_min_targets"  (default 2^13): at or above (FP64), 4 targets per thread, one CTA per SM;
  *   "few_max_targets"   (default 2048): at or below, the warps of a CTA share 32 targets and split the sources.
  *   "ring_min_tiles" / "ring_max_split" (defaults 1 / 64): shared-memory ring paths: shortest source chunk (in tiles) and

@@ -130,10 +130,11 @@ struct Options {
   int64_t const_banks = 2;
   int64_t const_ctas_per_sm = 6;
   int64_t const_ctas_per_sm_overlap = 1;
-  // FP32 on the constant-bank path: 0 never, 1 always (above const_min_targets), -1 (default) where it measured faster
-  // than the shared-memory ring with the packed FP32 loops (profiles/r2c_ab_rate32_packed_vs_scalar.md): Nt >= 2^17 for
-  // every kernel (at 2^15 the two are within a few per cent of each other either way), with const_banks_fp32 slices in
-  // flight (FP32 launches are half as long, so four slices hide their boundaries better)
+  // FP32 on the constant-bank path: 0 never, otherwise from const_min_targets like FP64.  With the packed FP32 loops,
+  // unrolled over 4 sources, it is the faster path from 2^15 targets for every kernel but Laplace3D_FxU, which is within
+  // 1 % there and 10 % ahead from 2^17 (profiles/r2c_ab_rate32_packed_vs_scalar.md, r2e_ab_rate32_const_shapes.md); round 1's
+  // scalar loops only won from 2^17.  const_banks_fp32 slices in flight (FP32 launches are half as long, so four slices hide
+  // their boundaries better).
   int64_t const_fp32 = -1;
   int64_t const_banks_fp32 = 4;
   // Above this many pairs Eval first runs the O(Ns+Nt) coincidence probe (coincidence.cuh) and lets the pair kernels
@@ -483,7 +484,7 @@ template <class Real, int KID, int RSQ>
 int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* v_src, const Real* r_trg, Real* v_trg, Real ctx0, cudaStream_t stream) {
   using Tn = Tune<Real>;
   constexpr int REC = RecTraits<Real, KID>::REC;
-  const bool fp32_const = g.opt.const_fp32 == 1 || (g.opt.const_fp32 < 0 && Nt >= (1 << 17));
+  const bool fp32_const = g.opt.const_fp32 != 0;
   const bool use_const = Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || fp32_const);
   // coincidence probe (big problems only): lets the pair kernels skip the r2 == 0 mask where it cannot matter
   const bool probe = g.opt.probe_min_pairs > 0 && (double)Ns * (double)Nt >= (double)g.opt.probe_min_pairs;

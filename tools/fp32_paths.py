@@ -40,7 +40,7 @@ def main():
         for lg in (15, 17, 20):
             Nt, Ns = 1 << lg, 1 << 18
             base = None
-            for name, opts in (("smem", dict(const_fp32=0)), ("const banks=2", dict(const_fp32=1, const_banks=2)), ("const banks=4", dict(const_fp32=1, const_banks=4))):
+            for name, opts in (("smem", dict(const_fp32=0)), ("const banks=2", dict(const_fp32=1, const_banks_fp32=2)), ("const banks=4", dict(const_fp32=1, const_banks_fp32=4))):
                 sb.reset_options()
                 for k, val in opts.items():
                     sb.set_option(k, val)
