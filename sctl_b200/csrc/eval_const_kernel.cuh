@@ -28,6 +28,10 @@
 #ifndef SCTL_CUDA_CONST_HOIST
 #define SCTL_CUDA_CONST_HOIST -1
 #endif
+//   SCTL_CUDA_CONST_SWP    1: software-pipelined FP64 loop (const_pair_loop_swp); 0 (default): the plain loop
+#ifndef SCTL_CUDA_CONST_SWP
+#define SCTL_CUDA_CONST_SWP 0
+#endif
 
 namespace sctl_cuda {
 
@@ -125,6 +129,39 @@ __device__ __forceinline__ void const_pair_loop(V (&acc)[T][KerTraits<KID>::K1],
   }
 }
 
+// Software-pipelined form of the FP64 loop (tuning build, SCTL_CUDA_CONST_SWP=1): the front half of group g+1 (loads,
+// dx, r2, seed) is issued between the back halves of group g, so no pair waits for its own MUFU / LDCU latency.
+template <int KID, int T, int RSQ, int U, bool MASK>
+__device__ __forceinline__ void const_pair_loop_swp(double (&acc)[T][KerTraits<KID>::K1], const double (&xt)[T][3], const double* src, int n) {
+  constexpr int REC = RecTraits<double, KID>::REC;
+  double dx[U][T][3], r2[U][T], y0[U][T];
+  int s = 0;
+  if (n >= U) {
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < T; j++) pair_front<RSQ, MASK>(dx[u][j], r2[u][j], y0[u][j], xt[j], src + u * REC);
+    for (s = U; s + U <= n; s += U) {
+#pragma unroll
+      for (int u = 0; u < U; u++)
+#pragma unroll
+        for (int j = 0; j < T; j++) {
+          pair_back<KID, RSQ>(acc[j], dx[u][j], r2[u][j], y0[u][j], src + (s - U + u) * REC);
+          pair_front<RSQ, MASK>(dx[u][j], r2[u][j], y0[u][j], xt[j], src + (s + u) * REC);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+#pragma unroll
+      for (int j = 0; j < T; j++) pair_back<KID, RSQ>(acc[j], dx[u][j], r2[u][j], y0[u][j], src + (s - U + u) * REC);
+  }
+  for (; s < n; s++) {
+    const double* rec = src + s * REC;
+#pragma unroll
+    for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec);
+  }
+}
+
 // FP32 pair loops run on packed values (two targets each)
 template <class Real, int KID, int T> __host__ __device__ constexpr bool const_packed() { return SCTL_CUDA_F32X2 && sizeof(Real) == 4 && T % 2 == 0; }
 
@@ -183,6 +220,9 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
         acc[2 * p][k] = acc2[p][k].v.x;
         acc[2 * p + 1][k] = acc2[p][k].v.y;
       }
+  } else if constexpr (SCTL_CUDA_CONST_SWP && sizeof(Real) == 8 && !KerNeedsCtx<KID>::value) {
+    if (unmasked) const_pair_loop_swp<KID, T, RSQ, U, false>(acc, xt, src, n);
+    else const_pair_loop_swp<KID, T, RSQ, U, true>(acc, xt, src, n);
   } else {
     // The refinement's loop-invariant operands (pair_math.cuh, rsqrt_masked): handed in as kernel arguments so that
     // ptxas cannot fold them back into literals.  One zero low word per unrolled pair: each then lives in the low half of

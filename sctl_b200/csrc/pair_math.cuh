@@ -531,6 +531,27 @@ __device__ __forceinline__ void pair_update(Real (&acc)[KerTraits<KID>::K1], con
   else PairApply<KID, Real>::run(acc, dx, rinv, s);
 }
 
+// The same pair in two halves, for loops that software-pipeline across sources (eval_const_kernel.cuh): the front half
+// ends at the seed (everything up to the MUFU), the back half refines it and applies the kernel.  pair_front + pair_back
+// perform exactly the operations of pair_update, in the same order per pair.
+template <int RSQ, bool MASK, class S>
+__device__ __forceinline__ void pair_front(double (&dx)[3], double& r2, double& y0, const double (&xt)[3], const S* s) {
+  dx[0] = xt[0] - s[0];
+  dx[1] = xt[1] - s[1];
+  dx[2] = xt[2] - s[2];
+  r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
+  y0 = rsqrt_masked<RSQ_SEED, MASK>(r2, 0, 0.0);
+}
+template <int KID, int RSQ, class S>
+__device__ __forceinline__ void pair_back(double (&acc)[KerTraits<KID>::K1], const double (&dx)[3], double r2, double y0, const S* s) {
+  double rinv = y0;
+  if (RSQ != RSQ_SEED) {
+    const double e = fma(-r2, y0 * y0, 1.0);
+    rinv = (RSQ == RSQ_NEWTON) ? y0 * fma(e, RSQ_NEWTON_B, RSQ_NEWTON_A) : y0 * fma(e, fma(e, 0.375, 0.5), 1.0);
+  }
+  PairApply<KID, double>::run(acc, dx, rinv, s);
+}
+
 // uKerMatrix twin: u[K0][K1] (unscaled) for one displacement, with the raw normal (KernelMatrix path,
 // generic-kernel.txx:213-329, never uses the fused apply).
 template <int KID, class Real> struct PairMatrix;
