@@ -218,6 +218,10 @@ int sctl_cuda_bio_create(sctl_cuda_direct_t far, int src, int trg, sctl_cuda_nea
 int sctl_cuda_bio_destroy(sctl_cuda_bio_t h);
 int sctl_cuda_bio_apply(sctl_cuda_bio_t h, int digits, const void* F, int64_t nF, const void* F_far_nodes, int64_t nF_far, void* U, int64_t nU);
 int sctl_cuda_bio_last_timing(sctl_cuda_bio_t h, double* far_ms, double* tail_ms, double* total_ms);
+/* Work items of the near-field GEMV that each GPU of the far-field session runs (items[p] for the p-th GPU, up to cap
+ * entries); all zero when the GEMV is not sharded (one GPU, no near session, or a block list whose U_near ranges do not
+ * follow the work-list order), in which case the near session's own GPU runs all of it. */
+int sctl_cuda_bio_near_shards(sctl_cuda_bio_t h, int64_t* items, int cap);
 
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
  *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64,

@@ -81,6 +81,7 @@ def load_library():
     L.sctl_cuda_bio_destroy.argtypes = [vp]
     L.sctl_cuda_bio_apply.argtypes = [vp, i, vp, i64, vp, i64, vp, i64]
     L.sctl_cuda_bio_last_timing.argtypes = [vp, dp, dp, dp]
+    L.sctl_cuda_bio_near_shards.argtypes = [vp, C.POINTER(i64), i]
     _lib = L
     return L
 
@@ -665,6 +666,12 @@ class BioApply:
         a, b, c = C.c_double(), C.c_double(), C.c_double()
         _check(load_library().sctl_cuda_bio_last_timing(self._h, C.byref(a), C.byref(b), C.byref(c)))
         return {"far_ms": a.value, "tail_ms": b.value, "total_ms": c.value}
+
+    def near_shards(self):
+        """Work items of the near-field GEMV per GPU of the far-field session (all zero: not sharded)."""
+        v = (C.c_int64 * 16)()
+        _check(load_library().sctl_cuda_bio_near_shards(self._h, v, 16))
+        return [int(x) for x in v][:len(self.far.devices())]
 
     def compute_potential_staged(self, F, F_far_nodes=None):
         F = np.ascontiguousarray(F, dtype=self._dtype).reshape(-1)

@@ -111,7 +111,8 @@ def test_particle_direct_follows_the_current_device(sb, cpu_oracle):
 
 def test_bio_apply_pipeline_two_gpus(sb, cpu_oracle):
     """The whole BoundaryIntegralOp apply with the far field sharded over 2 GPUs: the shards are collected on the first GPU
-    (peer copies), the near accumulation runs there; agrees with the 1-GPU pipeline to rounding and with the staged apply."""
+    (peer copies), the near-field GEMV is sharded too and the accumulation runs on the first GPU; agrees with the 1-GPU
+    pipeline to rounding and with the staged apply bit for bit."""
     _need_gpus(sb, 2)
     from sctl_b200 import synth
     from test_gpu_near import block_list, near_target_tables
@@ -131,6 +132,15 @@ def test_bio_apply_pipeline_two_gpus(sb, cpu_oracle):
         bio = sb.BioApply(sb.KERNELS[kernel], X_far, Xn_far, wts, Xtrg, None, digits=-1, n_gpus=n, near=near)
         res.append(bio.compute_potential(F))
         assert np.array_equal(res[-1], bio.compute_potential_staged(F))
+        # the near-field GEMV is sharded with the far field: every GPU runs a slice of its work list (same kernel and items,
+        # so the staged apply above, which runs all of it on the first GPU, gives the same bits)
+        shards = bio.near_shards()
+        assert len(shards) == n and (all(x > 0 for x in shards) if n > 1 else shards == [0]), shards
+        # a new matrix in the near session reaches the other GPUs' copies of their slices
+        near.set_matrix(2.0 * K_near)
+        assert np.array_equal(bio.compute_potential(F), bio.compute_potential_staged(F))
+        near.set_matrix(K_near)
+        assert np.array_equal(bio.compute_potential(F), res[-1])
         bio.close()
         near.close()
     assert rel_err(res[0], res[1]) <= 1e-13
