@@ -99,6 +99,14 @@ template <class Real> class BioApply {
     if (bio_) sctl_cuda_bio_last_timing(bio_, &far_ms, &tail_ms, &total_ms);
   }
 
+  // Work items of the near-field GEMV that each GPU of the far-field session ran in the last ComputePotential (items[p] for
+  // the p-th GPU; all zero: the near session's own GPU ran all of it).
+  std::vector<int64_t> NearShards() const {
+    std::vector<int64_t> items(16, 0);
+    if (bio_) sctl_cuda_bio_near_shards(bio_, items.data(), (int)items.size());
+    return items;
+  }
+
   // The same apply through the two sessions' host-array entries, phase after phase (the cross-check of the pipeline above).
   template <class VecOut, class VecIn> void ComputePotentialStaged(VecOut& U, const VecIn& F, const VecIn& F_far_nodes = VecIn()) {
     const VecIn& Fsrc = F_far_nodes.Dim() ? F_far_nodes : F;
