@@ -6,6 +6,7 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s line %d\n", cudaGetErrorString(e), __LINE__); exit(1);} } while (0)
 
 __constant__ float2 cpr[512];
+__constant__ float cs[64];
 
 // MODE 0: scalar FFMA, 3 distinct registers            (16 per iteration-unit)
 // MODE 1: FFMA2, 3 distinct 64-bit registers           (8 per unit = same flops)
@@ -16,6 +17,10 @@ __constant__ float2 cpr[512];
 // MODE 6: FFMA2 with one operand from the constant bank (uniform address)
 // MODE 7: FFMA2 x8 + 2 MUFU.RSQ + 8 ALU
 // MODE 8: scalar FFMA x16 + 2 MUFU.RSQ + 8 ALU
+// Round 2: the form the FP32 pair loops use -- one operand a SCALAR broadcast to both halves
+// MODE 9:  FFMA2 a = fma(b, s, a), s a 32-bit value from the constant bank at a uniform address (SASS: UR.F32 operand)
+// MODE 10: FFMA2 a = fma(b, s, a), s a 32-bit vector register (SASS: R.F32 operand)
+// MODE 11: FFMA2 a = fma(a, c, s), the scalar in the addend slot, from the constant bank
 template <int MODE> __global__ void __launch_bounds__(256) probe(int iters, const float* __restrict__ in, float* out) {
   float2 a[8], b[8], c[8];
   float r[2];
@@ -39,6 +44,9 @@ template <int MODE> __global__ void __launch_bounds__(256) probe(int iters, cons
         if (MODE == 2) a[i] = __ffma2_rn(b[i], b[i], a[i]);
         if (MODE == 3) a[i] = __ffma2_rn(a[i], m, cc);
         if (MODE == 6) a[i] = __ffma2_rn(b[i], cpr[(u * 8 + i)], a[i]);
+        if (MODE == 9) { const float sc = cs[(it & 1) * 32 + u * 8 + i]; a[i] = __ffma2_rn(b[i], make_float2(sc, sc), a[i]); }
+        if (MODE == 10) { const float sc = r[i & 1]; a[i] = __ffma2_rn(b[i], make_float2(sc, sc), a[i]); }
+        if (MODE == 11) { const float sc = cs[(it & 1) * 32 + u * 8 + i]; a[i] = __ffma2_rn(a[i], c[i], make_float2(sc, sc)); }
       }
       if (MODE == 4 || MODE == 5 || MODE == 7 || MODE == 8) {
         constexpr int NA = (MODE >= 7) ? 2 : 1;
@@ -82,12 +90,17 @@ int main() {
   float *in, *out; CK(cudaMalloc(&in, sizeof(h))); CK(cudaMalloc(&out, 64)); CK(cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice));
   float2 hc[512]; for (int i = 0; i < 512; i++) hc[i] = make_float2(1e-3f * i, 2e-3f * i);
   CK(cudaMemcpyToSymbol(cpr, hc, sizeof(hc)));
+  float hs[64]; for (int i = 0; i < 64; i++) hs[i] = 1e-3f * (i + 1);
+  CK(cudaMemcpyToSymbol(cs, hs, sizeof(hs)));
   printf("device %s, %d SMs\n", p.name, p.multiProcessorCount);
   run<0>("scalar FFMA 3 distinct", p.multiProcessorCount, in, out);
   run<1>("FFMA2 3 distinct", p.multiProcessorCount, in, out);
   run<2>("FFMA2 2 distinct", p.multiProcessorCount, in, out);
   run<3>("FFMA2 shared m,c", p.multiProcessorCount, in, out);
   run<6>("FFMA2 one operand from the constant bank", p.multiProcessorCount, in, out);
+  run<9>("FFMA2 scalar operand UR.F32 (constant bank, uniform)", p.multiProcessorCount, in, out);
+  run<10>("FFMA2 scalar operand R.F32 (vector register)", p.multiProcessorCount, in, out);
+  run<11>("FFMA2 scalar addend UR.F32", p.multiProcessorCount, in, out);
   run<4>("scalar FFMA x16 + 1 MUFU + 4 ALU", p.multiProcessorCount, in, out);
   run<5>("FFMA2 x8 + 1 MUFU + 4 ALU", p.multiProcessorCount, in, out);
   run<8>("scalar FFMA x16 + 2 MUFU + 8 ALU", p.multiProcessorCount, in, out);
