@@ -32,6 +32,12 @@
 #ifndef SCTL_CUDA_CONST_SWP
 #define SCTL_CUDA_CONST_SWP 0
 #endif
+//   SCTL_CUDA_CONST_PRAGMA_LOOP  1 (default): kernels without hoisted operands use `#pragma unroll U` over the sources;
+//                          0: the hand-blocked loop for them too.  Same instructions, but ptxas schedules the two forms
+//                          differently: Stokes3D_FxU FP64 807.7 vs 797.1 Gpair/s (profiles/r2b_ab_rate.md, third session)
+#ifndef SCTL_CUDA_CONST_PRAGMA_LOOP
+#define SCTL_CUDA_CONST_PRAGMA_LOOP 1
+#endif
 
 namespace sctl_cuda {
 
@@ -228,6 +234,25 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
     // ptxas cannot fold them back into literals.  One zero low word per unrolled pair: each then lives in the low half of
     // the register pair its MUFU.RSQ64H writes the high half of, for the whole loop.
     constexpr bool HOIST = ConstHoist<Real, KID>::value;
+    if constexpr (!HOIST && SCTL_CUDA_CONST_PRAGMA_LOOP) {
+      // no per-pair operands to hand in: the compiler's own partial unrolling of the plain loop, which ptxas schedules
+      // better than the hand-blocked form below (+1.3 % on Stokes3D_FxU)
+      if (unmasked) {
+#pragma unroll U
+        for (int s = 0; s < n; s++) {
+          const Real* rec = src + s * RecTraits<Real, KID>::REC;
+#pragma unroll
+          for (int j = 0; j < T; j++) pair_update<KID, RSQ, false>(acc[j], xt[j], rec, a.ctx0);
+        }
+      } else {
+#pragma unroll U
+        for (int s = 0; s < n; s++) {
+          const Real* rec = src + s * RecTraits<Real, KID>::REC;
+#pragma unroll
+          for (int j = 0; j < T; j++) pair_update<KID, RSQ, true>(acc[j], xt[j], rec, a.ctx0);
+        }
+      }
+    } else {
     int lo[U][T];
 #pragma unroll
     for (int u = 0; u < U; u++)
@@ -236,6 +261,7 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
     const Real k = HOIST ? a.rsq_k : (Real)rsq_poly_k<RSQ>();
     if (unmasked) const_pair_loop<Real, Real, KID, T, RSQ, U, false>(acc, xt, src, n, a.ctx0, lo, k);
     else const_pair_loop<Real, Real, KID, T, RSQ, U, true>(acc, xt, src, n, a.ctx0, lo, k);
+    }
   }
   if (gridDim.y > 1) {
     // grid.y == cluster size: rank 0 adds the other ranks' partial sums in rank order
