@@ -38,6 +38,10 @@
 #ifndef SCTL_CUDA_CONST_PRAGMA_LOOP
 #define SCTL_CUDA_CONST_PRAGMA_LOOP 1
 #endif
+//   SCTL_CUDA_CONST32_BLOCKED_LOOP  the same choice for the packed FP32 loops (1: hand-blocked)
+#ifndef SCTL_CUDA_CONST32_BLOCKED_LOOP
+#define SCTL_CUDA_CONST32_BLOCKED_LOOP 1
+#endif
 
 namespace sctl_cuda {
 
@@ -111,27 +115,38 @@ template <class Real, int KID> inline ConstGeom const_geometry(int64_t Ns, int64
   return g;
 }
 
-// U sources x T targets per iteration, unrolled by hand (not #pragma unroll U) so that every unrolled pair has its own
-// `lo` operand; the remainder (n % U sources) runs one source at a time.  `src` and `n` are warp-uniform: the records
-// are read with LDCU into uniform registers.  V is the type a pair is computed in: Real, or f32x2 (two targets per
-// value, packed FP32 instructions with the record's scalars as broadcast uniform operands; pair_math.cuh).
-template <class V, class Real, int KID, int T, int RSQ, int U, bool MASK>
+// U sources x T targets per iteration.  BLOCKED: unrolled by hand (not #pragma unroll U) so that every unrolled pair has
+// its own `lo` operand, the remainder (n % U sources) one source at a time -- the form the hoisted operands need.
+// Otherwise `#pragma unroll U` over the plain source loop: the same instructions, which ptxas schedules better (FP64
+// Stokes3D_FxU 807.7 vs 797.1 Gpair/s, profiles/r2b_ab_rate.md).  `src` and `n` are warp-uniform: the records are read
+// with LDCU into uniform registers.  V is the type a pair is computed in: Real, or f32x2 (two targets per value, packed
+// FP32 instructions with the record's scalars as broadcast uniform operands; pair_math.cuh).
+template <class V, class Real, int KID, int T, int RSQ, int U, bool MASK, bool BLOCKED>
 __device__ __forceinline__ void const_pair_loop(V (&acc)[T][KerTraits<KID>::K1], const V (&xt)[T][3], const Real* src, int n, V ctx0,
                                                 const int (&lo)[U][T], V k) {
   constexpr int REC = RecTraits<Real, KID>::REC;
-  int s = 0;
-  for (; s + U <= n; s += U) {
+  if constexpr (BLOCKED) {
+    int s = 0;
+    for (; s + U <= n; s += U) {
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const Real* rec = src + (s + u) * REC;  // uniform address: LDCU into uniform registers
+      for (int u = 0; u < U; u++) {
+        const Real* rec = src + (s + u) * REC;  // uniform address: LDCU into uniform registers
 #pragma unroll
-      for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, ctx0, lo[u][j], k);
+        for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, ctx0, lo[u][j], k);
+      }
     }
-  }
-  for (; s < n; s++) {
-    const Real* rec = src + s * REC;
+    for (; s < n; s++) {
+      const Real* rec = src + s * REC;
 #pragma unroll
-    for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, ctx0, lo[0][j], k);
+      for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, ctx0, lo[0][j], k);
+    }
+  } else {
+#pragma unroll U
+    for (int s = 0; s < n; s++) {
+      const Real* rec = src + s * REC;
+#pragma unroll
+      for (int j = 0; j < T; j++) pair_update<KID, RSQ, MASK>(acc[j], xt[j], rec, ctx0, lo[0][j], k);
+    }
   }
 }
 
@@ -217,8 +232,9 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
 #pragma unroll
       for (int k = 0; k < K1; k++) acc2[p][k] = f32x2(0.0f);
     }
-    if (unmasked) const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, false>(acc2, xt2, src, n, f32x2((float)a.ctx0), lo, f32x2(0.0f));
-    else const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, true>(acc2, xt2, src, n, f32x2((float)a.ctx0), lo, f32x2(0.0f));
+    constexpr bool BLOCKED = SCTL_CUDA_CONST32_BLOCKED_LOOP != 0;
+    if (unmasked) const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, false, BLOCKED>(acc2, xt2, src, n, f32x2((float)a.ctx0), lo, f32x2(0.0f));
+    else const_pair_loop<f32x2, Real, KID, T / 2, RSQ, U, true, BLOCKED>(acc2, xt2, src, n, f32x2((float)a.ctx0), lo, f32x2(0.0f));
 #pragma unroll
     for (int p = 0; p < T / 2; p++)
 #pragma unroll
@@ -234,34 +250,15 @@ __global__ void __launch_bounds__(NT, MINB) eval_pairs_const_kernel(const ConstE
     // ptxas cannot fold them back into literals.  One zero low word per unrolled pair: each then lives in the low half of
     // the register pair its MUFU.RSQ64H writes the high half of, for the whole loop.
     constexpr bool HOIST = ConstHoist<Real, KID>::value;
-    if constexpr (!HOIST && SCTL_CUDA_CONST_PRAGMA_LOOP) {
-      // no per-pair operands to hand in: the compiler's own partial unrolling of the plain loop, which ptxas schedules
-      // better than the hand-blocked form below (+1.3 % on Stokes3D_FxU)
-      if (unmasked) {
-#pragma unroll U
-        for (int s = 0; s < n; s++) {
-          const Real* rec = src + s * RecTraits<Real, KID>::REC;
-#pragma unroll
-          for (int j = 0; j < T; j++) pair_update<KID, RSQ, false>(acc[j], xt[j], rec, a.ctx0);
-        }
-      } else {
-#pragma unroll U
-        for (int s = 0; s < n; s++) {
-          const Real* rec = src + s * RecTraits<Real, KID>::REC;
-#pragma unroll
-          for (int j = 0; j < T; j++) pair_update<KID, RSQ, true>(acc[j], xt[j], rec, a.ctx0);
-        }
-      }
-    } else {
+    constexpr bool BLOCKED = HOIST || !SCTL_CUDA_CONST_PRAGMA_LOOP;
     int lo[U][T];
 #pragma unroll
     for (int u = 0; u < U; u++)
 #pragma unroll
       for (int j = 0; j < T; j++) lo[u][j] = HOIST ? a.zero : 0;
     const Real k = HOIST ? a.rsq_k : (Real)rsq_poly_k<RSQ>();
-    if (unmasked) const_pair_loop<Real, Real, KID, T, RSQ, U, false>(acc, xt, src, n, a.ctx0, lo, k);
-    else const_pair_loop<Real, Real, KID, T, RSQ, U, true>(acc, xt, src, n, a.ctx0, lo, k);
-    }
+    if (unmasked) const_pair_loop<Real, Real, KID, T, RSQ, U, false, BLOCKED>(acc, xt, src, n, a.ctx0, lo, k);
+    else const_pair_loop<Real, Real, KID, T, RSQ, U, true, BLOCKED>(acc, xt, src, n, a.ctx0, lo, k);
   }
   if (gridDim.y > 1) {
     // grid.y == cluster size: rank 0 adds the other ranks' partial sums in rank order
