@@ -21,7 +21,8 @@ def main():
     n = 1 << (int(sys.argv[2]) if len(sys.argv) > 2 else 19)
     sb.load_library()
     peak = sb.fma_peak(8, 300.0)
-    for kernel in ("Stokes3D_FxU", "Laplace3D_FxU", "Stokes3D_DxU"):
+    kernels = os.environ.get("AB_KERNELS", "Stokes3D_FxU,Laplace3D_FxU,Stokes3D_DxU").split(",")
+    for kernel in kernels:
         k0, k1, nd = DIMS[kernel]
         r_src, n_src, v_src, r_trg = synth.cube(n, n, k0, nd)
         d = [None if a is None else torch.from_numpy(a).cuda() for a in (r_src, n_src, v_src, r_trg)]
