@@ -74,11 +74,16 @@ template <class Real> struct ConstEvalArgs {
 // 10 IMAD.MOV per 8 pairs from the loop, but those issue in the FP64 pipe's shadow and what decides is how ptxas then
 // schedules the loop (the hoisted operands also need the hand-blocked loop form, const_pair_loop).  Chosen per kernel from
 // measurements on B200 (profiles/r2b_ab_rate.md, 2^19 x 2^19, digits -1 / 11, against the plain loop): Laplace3D_FxU
-// +1.9 % / +0.6 %, Laplace3D_FxdU +1.6 % / +1.8 %, Stokes3D_FSxU +0.2 % / +1.4 %; Stokes3D_FxU -1.3 % / -0.1 %,
-// Stokes3D_DxU, Laplace3D_DxU, Stokes3D_FxUP, Laplace3D_DxdU, BiotSavart3D_FxU -0.3 ... -2 %.
+// +1.9 % / +0.6 %, Laplace3D_FxdU +1.6 % / +1.8 %, Stokes3D_FSxU +0.2 % / +1.4 %, Laplace3D_Fxd2U +1.0 % / +1.6 %,
+// BiotSavart3D_FxdU +2.2 % / +0.2 %, Helmholtz3D_DxU +0.8 % / +0.3 %, HelmholtzDiff3D_FxdU 0 / +1.2 %; Stokes3D_FxU
+// -1.3 % / -0.1 %, Stokes3D_DxU, Laplace3D_DxU, Stokes3D_FxUP, Laplace3D_DxdU, BiotSavart3D_FxU -0.3 ... -2 %, Stokes3D_FxT,
+// Helmholtz3D_FxU and Helmholtz3D_FxdU one way at digits -1 and the other at 11.
+template <int KID> constexpr bool const_hoist_measured_faster() {
+  return KID == LAPLACE3D_FXU || KID == LAPLACE3D_FXDU || KID == STOKES3D_FSXU || KID == LAPLACE3D_FXD2U || KID == BIOTSAVART3D_FXDU || KID == HELMHOLTZ3D_DXU ||
+         KID == HELMHOLTZDIFF3D_FXDU;
+}
 template <class Real, int KID> struct ConstHoist {
-  static constexpr bool value = SCTL_CUDA_CONST_HOIST < 0 ? (sizeof(Real) == 8 && (KID == LAPLACE3D_FXU || KID == LAPLACE3D_FXDU || KID == STOKES3D_FSXU))
-                                                          : (SCTL_CUDA_CONST_HOIST != 0);
+  static constexpr bool value = SCTL_CUDA_CONST_HOIST < 0 ? (sizeof(Real) == 8 && const_hoist_measured_faster<KID>()) : (SCTL_CUDA_CONST_HOIST != 0);
 };
 
 template <class Real, int KID> constexpr int const_chunk_records() { return CONST_PACK_BYTES / (RecTraits<Real, KID>::REC * (int)sizeof(Real)); }

@@ -28,14 +28,15 @@ def main():
         d = [None if a is None else torch.from_numpy(a).cuda() for a in (r_src, n_src, v_src, r_trg)]
         for digits in (-1, 11):
             v = torch.zeros(n * k1, dtype=torch.float64, device="cuda")
-            sb.eval_device(kernel, d[0], d[1], d[2], d[3], v, digits=digits)
+            ctx = 1.7 if "Helmholtz" in kernel else None
+            sb.eval_device(kernel, d[0], d[1], d[2], d[3], v, digits=digits, ctx=ctx)
             torch.cuda.synchronize()
             chk = float(v.double().sum())
             ts = []
             for _ in range(4):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                sb.eval_device(kernel, d[0], d[1], d[2], d[3], v, digits=digits)
+                sb.eval_device(kernel, d[0], d[1], d[2], d[3], v, digits=digits, ctx=ctx)
                 e1.record()
                 torch.cuda.synchronize()
                 ts.append(e0.elapsed_time(e1))
