@@ -8,3 +8,4 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/r2_smoke_fin
 timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $O/r2_bench_reference_arm_final.json 2>$O/r2_bench_ref.err; echo "ref rc=$?"; cut -c1-300 $O/r2_bench_reference_arm_final.json
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/r2_bench_n1_final.json 2>$O/r2_bench_n1.err; echo "bench rc=$?"; cat $O/r2_bench_n1_final.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 1200 --csv --log-file $O/r2_launches_bench_final.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > $O/r2_launches_bench_final.out 2>&1; echo "launch list rc=$?"
+timeout 900 python tools/rate_table.py > $O/r2_rate_table_final.md 2>$O/r2_rate_table_final.err; echo "rate table rc=$?"
