@@ -253,6 +253,13 @@ int sctl_cuda_reset_options(void);
 int sctl_cuda_const_geometry(int kernel_id, int real_bytes, int64_t Ns, int64_t Nt, int banks_wanted, int* banks, int* chunk, int* row_words,
                              int* bank_stride, int* rec_bytes, int64_t* seg_bytes, int64_t* n_chunks);
 
+/* Test hook: the slices the multi-GPU apply pipeline cuts the near-field GEMV into for a block list (columns as in
+ * sctl_cuda_near_create) and n_gpus GPUs.  slices: 6 values per GPU -- items [i0, i1) of the GEMV work list, Reals of K read
+ * [klo, khi), Reals of U_near written [ulo, uhi); n_items: length of the work list.  Returns 0, or -1 when the block list
+ * cannot be sharded (its U_near ranges do not follow the work-list order). */
+int sctl_cuda_plan_near_slices(int real_bytes, int k0, int k1, int64_t n_blk, const int64_t* ns, const int64_t* u_dsp, const int64_t* nt, const int64_t* k_dsp, int n_gpus,
+                               int64_t* slices, int64_t* n_items);
+
 /* The grid planner, exposed for host-side tests (no GPU needed): for Nt targets in blocks of `tpb`, Ns sources
  * and `slots` resident CTAs (SMs x CTAs/SM) returns the number of source chunks, their length and the fraction
  * of the last wave that does useful work. */

@@ -76,6 +76,7 @@ def load_library():
     L.sctl_cuda_near_apply.argtypes = [vp, vp, i64, vp, i64]
     L.sctl_cuda_near_set_targets.argtypes = [vp, i64, p64, p64, i64, p64]
     L.sctl_cuda_near_apply_accumulate.argtypes = [vp, vp, i64, vp, i64]
+    L.sctl_cuda_plan_near_slices.argtypes = [i, i, i, i64, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), i, C.POINTER(i64), C.POINTER(i64)]
     L.sctl_cuda_plan_eval.argtypes = [i64, i64, i, i, i, i, C.POINTER(i64), ip, C.POINTER(i64), dp]
     L.sctl_cuda_bio_create.argtypes = [vp, i, i, vp, i, vp, i64, vp, i64, C.POINTER(vp)]
     L.sctl_cuda_bio_destroy.argtypes = [vp]
@@ -142,6 +143,21 @@ def kernel_info(kernel):
     sc, nm = C.c_double(), C.c_char_p()
     _check(L.sctl_cuda_kernel_info(_kid(kernel), C.byref(k0), C.byref(k1), C.byref(nd), C.byref(fl), C.byref(fa), C.byref(sc), C.byref(nm)))
     return dict(k0=k0.value, k1=k1.value, nd=nd.value, flops=fl.value, f_alg=fa.value, scale=sc.value, name=nm.value.decode())
+
+
+def plan_near_slices(real_bytes, k0, k1, ns, u_dsp, nt, k_dsp, n_gpus):
+    """The slices the multi-GPU apply pipeline cuts the near-field GEMV into (host logic, no GPU needed): a list of dicts
+    (i0, i1, klo, khi, ulo, uhi) per GPU, the length of the work list, and whether the block list can be sharded at all."""
+    cols = [np.ascontiguousarray(a, dtype=np.int64) for a in (ns, u_dsp, nt, k_dsp)]
+    n_blk = cols[0].size
+    out = np.zeros(6 * n_gpus, dtype=np.int64)
+    n_items = C.c_int64()
+    p64 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+    rc = load_library().sctl_cuda_plan_near_slices(real_bytes, k0, k1, n_blk, *[p64(a) for a in cols], n_gpus, p64(out), C.byref(n_items))
+    if rc > 0:
+        _check(rc)
+    keys = ("i0", "i1", "klo", "khi", "ulo", "uhi")
+    return [dict(zip(keys, (int(x) for x in out[6 * p:6 * p + 6]))) for p in range(n_gpus)], n_items.value, rc == 0
 
 
 def last_timing():

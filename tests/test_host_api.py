@@ -210,3 +210,57 @@ def test_planners_hold_their_invariants_on_random_sizes(sbm):
 
     ring()
     bank()
+
+
+def test_near_slice_planner_tiles_the_work_list(sbm):
+    """Property test (hypothesis) of the host logic that shards the near-field GEMV of a multi-GPU apply (csrc/near_session.inc
+    plan_near_slices): whatever the element sizes, the slices tile the work list exactly and in order, every item's rows of
+    K and U_near lie inside its slice's ranges, the U_near ranges of different slices do not overlap, and the bytes of K are
+    balanced to within one item; a block list whose U_near ranges do not follow the work-list order is refused."""
+    from hypothesis import given, settings, strategies as st
+
+    def block_table(nds, near, blk, k0, k1):
+        # BoundaryIntegralOp's layout (boundary_integral.txx:1009-1032): per element, blocks of at most blk near targets
+        nds, near = np.asarray(nds), np.asarray(near)
+        near_dsp = np.concatenate([[0], np.cumsum(near)[:-1]])
+        K_dsp = np.concatenate([[0], np.cumsum(nds * near)[:-1]])
+        ns, u_dsp, nt, k_dsp = [], [], [], []
+        for e in range(len(nds)):
+            for t0 in range(0, near[e], blk):
+                ns.append(nds[e]); u_dsp.append(near_dsp[e] + t0); nt.append(min(blk, near[e] - t0)); k_dsp.append(K_dsp[e] * k0 * k1 + t0 * k1 * nds[e] * k0)
+        return [np.array(c, dtype=np.int64) for c in (ns, u_dsp, nt, k_dsp)]
+
+    @settings(max_examples=200, deadline=None)
+    @given(elems=st.lists(st.tuples(st.integers(0, 70), st.integers(0, 150)), min_size=1, max_size=40), blk=st.integers(1, 64),
+           dims=st.sampled_from([(1, 1), (3, 3), (1, 3), (2, 6)]), P=st.integers(1, 8), rb=st.sampled_from([8, 4]))
+    def check(elems, blk, dims, P, rb):
+        k0, k1 = dims
+        ns, u_dsp, nt, k_dsp = block_table([e[0] for e in elems], [e[1] for e in elems], blk, k0, k1)
+        slices, n_items, ok = sbm.plan_near_slices(rb, k0, k1, ns, u_dsp, nt, k_dsp, P)
+        assert ok
+        rows_per_item = 32 if rb == 8 else 64
+        items = [(b, r) for b in range(len(nt)) for r in range(0, int(nt[b]) * k1, rows_per_item)]
+        assert n_items == len(items)
+        assert slices[0]["i0"] == 0 and slices[-1]["i1"] == n_items and all(slices[p]["i1"] == slices[p + 1]["i0"] for p in range(P - 1))
+        total = sum((min(int(nt[b]) * k1, r + rows_per_item) - r) * int(ns[b]) * k0 for b, r in items)
+        biggest = max([(min(int(nt[b]) * k1, r + rows_per_item) - r) * int(ns[b]) * k0 for b, r in items] + [0])
+        prev_uhi = 0
+        for p, sl in enumerate(slices):
+            mine = items[sl["i0"]:sl["i1"]]
+            size = 0
+            for b, r in mine:
+                r1 = min(int(nt[b]) * k1, r + rows_per_item)
+                cols = int(ns[b]) * k0
+                assert sl["klo"] <= int(k_dsp[b]) + r * cols and int(k_dsp[b]) + r1 * cols <= sl["khi"]
+                assert sl["ulo"] <= int(u_dsp[b]) * k1 + r and int(u_dsp[b]) * k1 + r1 <= sl["uhi"]
+                size += (r1 - r) * cols
+            if mine:
+                assert sl["ulo"] >= prev_uhi
+                prev_uhi = sl["uhi"]
+            assert size <= total / P + biggest + 1
+
+    check()
+    # two blocks whose U_near ranges run against the work-list order: refused, nothing sharded
+    ns, u_dsp, nt, k_dsp = [np.array(c, dtype=np.int64) for c in ([5, 5], [40, 0], [40, 40], [0, 200])]
+    slices, n_items, ok = sbm.plan_near_slices(8, 1, 1, ns, u_dsp, nt, k_dsp, 2)
+    assert not ok and all(sl["i1"] == sl["i0"] == 0 for sl in slices)
