@@ -226,6 +226,8 @@ int sctl_cuda_bio_near_shards(sctl_cuda_bio_t h, int64_t* items, int cap);
 /* Tuning knobs (process-wide).  Eval picks its kernel by target count:
  *   "const_min_targets" (default 2^15): at or above, sources are streamed through the constant bank in chunks (FP64,
  *                       and FP32 unless "const_fp32" is 0, which keeps FP32 on the shared-memory ring);
+ *   "const_min_launch_flop" (default 5e8): ... and, in FP64, only if one launch of that path carries at least this much
+ *                       work (records per launch x targets x F_alg): cheap kernels switch at 2^16 targets;
  *   "wide_min_targets"  (default 2^13): at or above (FP64), 4 targets per thread, one CTA per SM;
  *   "few_max_targets"   (default 2048): at or below, the warps of a CTA share 32 targets and split the sources.
  *   "ring_min_tiles" / "ring_max_split" (defaults 1 / 64): shared-memory ring paths: shortest source chunk (in tiles) and

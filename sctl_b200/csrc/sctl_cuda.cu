@@ -120,6 +120,8 @@ struct Options {
   //   Nt >= wide_min_targets  : shared-memory ring, 4 targets per thread, one CTA per SM
   //   otherwise               : shared-memory ring, 2 targets per thread, two CTAs per SM
   int64_t const_min_targets = 1 << 15;
+  // ... and (FP64) only when one launch carries at least this much work: records per launch x targets x F_alg
+  int64_t const_min_launch_flop = 500000000LL;
   int64_t few_max_targets = 2048;
   // shared-memory ring: shortest source chunk (in tiles) the grid planner may give a CTA when it splits the sources
   int64_t ring_min_tiles = 1;
@@ -485,13 +487,17 @@ int eval_device_t(int dev, int64_t Ns, int64_t Nt, const Real* r_src, const Real
   using Tn = Tune<Real>;
   constexpr int REC = RecTraits<Real, KID>::REC;
   const bool fp32_const = g.opt.const_fp32 != 0;
-  const bool use_const = Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || fp32_const);
+  bool use_const = Nt >= g.opt.const_min_targets && (sizeof(Real) == 8 || fp32_const);
   // coincidence probe (big problems only): lets the pair kernels skip the r2 == 0 mask where it cannot matter
   const bool probe = g.opt.probe_min_pairs > 0 && (double)Ns * (double)Nt >= (double)g.opt.probe_min_pairs;
   ConstGeom cg = {};
   // the bit rows are part of the layout whether or not this call fills them: the chunk length, and with it the summation
   // order, must not depend on the probe options (masked and probed runs are bit-identical)
   if (use_const) cg = const_geometry<Real, KID>(Ns, const_target_blocks<Real>(Nt), const_banks_wanted<Real>(), true);
+  // FP64: a launch of the constant-bank path must carry enough work to pay for itself.  Measured on B200 at 2^15 targets
+  // (profiles/r2_small_shard_paths.md): the ring wins by 7 % / 5 % for Laplace3D_FxU / Stokes3D_DxU (3.6e8 / 4.0e8 flop per
+  // launch), the constant bank by 1 % / 4 % for Laplace3D_FxdU / Stokes3D_FxU (6.0e8 / 6.4e8); from 2^16 it wins for all.
+  if (use_const && sizeof(Real) == 8 && (double)cg.chunk * (double)Nt * KerTraits<KID>::F_ALG < (double)g.opt.const_min_launch_flop) use_const = false;
   const bool use_bits = use_const && cg.row_words && probe && g.opt.probe_per_block != 0;
   // packed sources: contiguous records, or chunk segments (records + coincidence bits) for the constant-bank path
   const size_t pack_bytes = use_const ? (size_t)cg.n_chunks * cg.seg_bytes : sizeof(Real) * (size_t)Ns * REC;
@@ -1227,6 +1233,7 @@ int sctl_cuda_set_option(const char* name, int64_t value) {
   if (!name) return fail("null option name");
   std::lock_guard<std::mutex> lk(g.mu);
   if (!strcmp(name, "const_min_targets")) g.opt.const_min_targets = value;
+  else if (!strcmp(name, "const_min_launch_flop")) g.opt.const_min_launch_flop = value;
   else if (!strcmp(name, "few_max_targets")) g.opt.few_max_targets = value;
   else if (!strcmp(name, "ring_min_tiles")) g.opt.ring_min_tiles = std::max<int64_t>(1, value);
   else if (!strcmp(name, "ring_max_split")) g.opt.ring_max_split = std::max<int64_t>(1, std::min<int64_t>(value, 1024));

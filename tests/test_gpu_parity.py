@@ -246,7 +246,7 @@ def test_every_eval_path_agrees(sb, cpu_oracle, kernel, dtype):
     want = cpu_oracle.eval(kernel, r_src, n_src, v_src, r_trg, dtype=dtype)
     big = 1 << 40
     paths = {"few": dict(few_max_targets=big, wide_min_targets=big, const_min_targets=big), "main": dict(few_max_targets=0, wide_min_targets=big, const_min_targets=big),
-             "wide": dict(few_max_targets=0, wide_min_targets=1, const_min_targets=big), "const": dict(few_max_targets=0, wide_min_targets=big, const_min_targets=1, const_fp32=1)}
+             "wide": dict(few_max_targets=0, wide_min_targets=1, const_min_targets=big), "const": dict(few_max_targets=0, wide_min_targets=big, const_min_targets=1, const_min_launch_flop=0, const_fp32=1)}
     try:
         for name, opts in paths.items():
             for k, v in opts.items():
@@ -283,7 +283,7 @@ def test_coincidence_probe_keeps_the_mask_when_needed(sb, cpu_oracle, kernel, dt
     und_s, und_t = r_src.copy(), r_trg.copy()
     und_s[3 * 77:3 * 77 + 3] = [0.0, tiny, -tiny]; und_t[3 * 99:3 * 99 + 3] = [tiny, 0.0, 2 * tiny]  # distinct, r2 underflows to 0
     variants["underflow"] = (und_s, und_t)
-    opts = {"ring": {}, "const": dict(const_min_targets=1, const_fp32=1), "const_global_flag": dict(const_min_targets=1, const_fp32=1, probe_per_block=0)}[path]
+    opts = {"ring": {}, "const": dict(const_min_targets=1, const_min_launch_flop=0, const_fp32=1), "const_global_flag": dict(const_min_targets=1, const_min_launch_flop=0, const_fp32=1, probe_per_block=0)}[path]
     try:
         for name, (src, trg) in variants.items():
             sb.reset_options()

@@ -52,17 +52,17 @@ def main():
         Nt = 1 << lg if lg < 64 else lg  # small numbers are exponents, large ones literal target counts
         Ns = 1 << args.ns if args.ns else Nt
         base = None
-        cfgs = [("const banks=1 cta/sm=6", dict(const_min_targets=1, const_banks=1, const_ctas_per_sm=6)),
-                ("const banks=2 ov=1", dict(const_min_targets=1, const_banks=2, const_ctas_per_sm_overlap=1)),
-                ("const banks=2 ov=2", dict(const_min_targets=1, const_banks=2, const_ctas_per_sm_overlap=2)),
-                ("const banks=4 ov=1", dict(const_min_targets=1, const_banks=4, const_ctas_per_sm_overlap=1)),
+        cfgs = [("const banks=1 cta/sm=6", dict(const_min_targets=1, const_min_launch_flop=0, const_banks=1, const_ctas_per_sm=6)),
+                ("const banks=2 ov=1", dict(const_min_targets=1, const_min_launch_flop=0, const_banks=2, const_ctas_per_sm_overlap=1)),
+                ("const banks=2 ov=2", dict(const_min_targets=1, const_min_launch_flop=0, const_banks=2, const_ctas_per_sm_overlap=2)),
+                ("const banks=4 ov=1", dict(const_min_targets=1, const_min_launch_flop=0, const_banks=4, const_ctas_per_sm_overlap=1)),
                 ("smem wide(T=4)", dict(const_min_targets=1 << 40, wide_min_targets=1, few_max_targets=0)),
                 ("smem main(T=2)", dict(const_min_targets=1 << 40, wide_min_targets=1 << 40, few_max_targets=0)),
                 ("smem few", dict(const_min_targets=1 << 40, wide_min_targets=1 << 40, few_max_targets=1 << 40))]
         if args.all_banks:
-            cfgs[3:3] = [("const banks=2 ov=4", dict(const_min_targets=1, const_banks=2, const_ctas_per_sm_overlap=4)),
-                         ("const banks=3 ov=1", dict(const_min_targets=1, const_banks=3, const_ctas_per_sm_overlap=1)),
-                         ("const banks=4 ov=2", dict(const_min_targets=1, const_banks=4, const_ctas_per_sm_overlap=2))]
+            cfgs[3:3] = [("const banks=2 ov=4", dict(const_min_targets=1, const_min_launch_flop=0, const_banks=2, const_ctas_per_sm_overlap=4)),
+                         ("const banks=3 ov=1", dict(const_min_targets=1, const_min_launch_flop=0, const_banks=3, const_ctas_per_sm_overlap=1)),
+                         ("const banks=4 ov=2", dict(const_min_targets=1, const_min_launch_flop=0, const_banks=4, const_ctas_per_sm_overlap=2))]
         for name, opts in cfgs:
             for k, val in opts.items():
                 sb.set_option(k, val)

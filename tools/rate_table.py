@@ -52,7 +52,7 @@ def main():
         print("\n| Nt | Ns | path | ms | Gpair/s | F_alg frac |\n|---|---|---|---|---|---|")
         for lg in (16, 17, 18, 19):
             Nt, Ns = 1 << lg, 1 << 18
-            for name, opts in (("const", dict(const_min_targets=1, wide_min_targets=1 << 40)), ("wide(T=4)", dict(const_min_targets=1 << 40, wide_min_targets=1)),
+            for name, opts in (("const", dict(const_min_targets=1, const_min_launch_flop=0, wide_min_targets=1 << 40)), ("wide(T=4)", dict(const_min_targets=1 << 40, wide_min_targets=1)),
                                ("main(T=2)", dict(const_min_targets=1 << 40, wide_min_targets=1 << 40))):
                 for k, val in opts.items():
                     sb.set_option(k, val)
