@@ -1,8 +1,19 @@
 // KernelMatrix on one B200:  M[(s*K0+k0)*ldM + t*K1+k1] = scale * u_{k0,k1}(x_t - x_s, n_s), overwriting.
 // Replaces GenericKernel<uKernel>::KernelMatrix (reference: include/sctl/generic-kernel.txx:213-329; layout
-// :268,306).  Store-bound: 8*K0*K1 bytes written per pair against ~25 flop, so the kernel is shaped for the
-// write stream -- one CTA owns BT consecutive targets of a few source rows, the K0 x K1 blocks of a row are
-// staged through shared memory and written out as contiguous, fully coalesced row segments.
+// :268,306).  Store-bound: sizeof(Real)*K0*K1 bytes written per pair against 13..50 flop, so the kernel is shaped for
+// the HBM write stream:
+//   * a CTA owns BT*T consecutive targets (register-resident, T per thread) of a contiguous range of source rows, so
+//     every matrix row it touches is one contiguous segment of BT*T*K1 Reals;
+//   * every global store is a 16-byte vector.  DIRECT (K1 == 1, M and the row pitch 16-byte aligned; chosen by the
+//     host): a thread's T = 16/sizeof(Real) consecutive targets are one vector, stored straight from registers (a warp
+//     writes 512 contiguous bytes per instruction).  Otherwise the K0 x (T*K1) values of a thread are staged through
+//     shared memory and the row segments are written out as aligned vectors, scalar elements only before the first and
+//     after the last 16-byte boundary of a segment -- rows need not be 16-byte aligned (odd ldM, matrix views), the
+//     staging index is shifted per row so that the shared-memory side of every vector is aligned too;
+//   * source coordinates (and normals) of a tile of rows are brought into shared memory by the whole CTA before the
+//     tile's rows are computed, so the row loop has no global load in it (round 1's kernel loaded them per row and
+//     spent its time on the long scoreboard: profiles/r1_ncu_kernel_matrix.md, 62 % / 40 % of the HBM copy bandwidth
+//     for Laplace3D_FxU FP64 / FP32).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -11,49 +22,119 @@
 
 namespace sctl_cuda {
 
-template <class Real, int KID, int RSQ, int BT>
-__global__ void __launch_bounds__(BT) kernel_matrix_kernel(int64_t Ns, int64_t Nt, const Real* __restrict__ r_src, const Real* __restrict__ n_src,
-                                                         const Real* __restrict__ r_trg, Real* __restrict__ M, int64_t ldM, Real scale, Real mu) {
+constexpr int KMAT_BT = 128;      // threads per CTA
+constexpr int KMAT_SRC_TILE = 32;  // source rows whose coordinates are staged together
+
+template <class Real> struct KmatVec;
+template <> struct KmatVec<double> { using type = double2; };
+template <> struct KmatVec<float> { using type = float4; };
+
+// Targets per thread: K1 == 1 -> one 16-byte vector of consecutive targets; K1 > 1 -> 8 bytes' worth of targets (the
+// staging buffer holds K0 * BT * T * K1 Reals: 27 KB for the K0 x K1 = 3 x 9 kernels in either precision).
+template <class Real, int KID> struct KmatShape {
+  static constexpr int V = 16 / (int)sizeof(Real);
+  static constexpr int T = KerTraits<KID>::K1 == 1 ? V : 8 / (int)sizeof(Real);
+};
+
+template <class Real, int KID, int RSQ, bool DIRECT>
+__global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int64_t Nt, int64_t rows_per_cta, const Real* __restrict__ r_src, const Real* __restrict__ n_src,
+                                                              const Real* __restrict__ r_trg, Real* __restrict__ M, int64_t ldM, Real scale, Real mu) {
   constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
-  __shared__ Real stage[K0][BT * K1 + 1];
-  const int64_t t_blk = (int64_t)blockIdx.x * BT;
-  const int64_t t = t_blk + threadIdx.x;
-  const int nt_blk = (int)((Nt - t_blk) < BT ? (Nt - t_blk) : BT);
-  Real xt[3] = {0, 0, 0};
-  if (t < Nt) {
+  constexpr int BT = KMAT_BT, SB = KMAT_SRC_TILE, V = KmatShape<Real, KID>::V, T = KmatShape<Real, KID>::T;
+  constexpr int W = BT * T * K1;  // columns of a row segment
+  using Vec = typename KmatVec<Real>::type;
+  __shared__ Real xs_s[SB][3];
+  __shared__ Real ns_s[ND ? SB : 1][3];
+  static_assert(!DIRECT || (K1 == 1 && T == V), "the direct path stores one vector of consecutive targets per row");
+  __shared__ __align__(16) Real stage[DIRECT ? 1 : K0][DIRECT ? V : W + V];
+
+  const int64_t t_blk = (int64_t)blockIdx.x * (BT * T);
+  const int64_t t0 = t_blk + (int64_t)threadIdx.x * T;
+  Real xt[T][3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) xt[k] = r_trg[t * 3 + k];
-  }
-  for (int64_t s = blockIdx.y; s < Ns; s += gridDim.y) {
-    Real dx[3], n[3] = {0, 0, 0};
+  for (int j = 0; j < T; j++)
 #pragma unroll
-    for (int k = 0; k < 3; k++) dx[k] = xt[k] - r_src[s * 3 + k];
-    if (ND) {
-#pragma unroll
-      for (int k = 0; k < 3; k++) n[k] = n_src[s * 3 + k];
+    for (int k = 0; k < 3; k++) xt[j][k] = (t0 + j < Nt) ? r_trg[(t0 + j) * 3 + k] : (Real)0;
+  const int n_col = (int)(((Nt - t_blk) < BT * T ? (Nt - t_blk) : BT * T) * K1);  // valid columns of this CTA's segments
+  const int64_t s_begin = (int64_t)blockIdx.y * rows_per_cta;
+  const int64_t s_end = (s_begin + rows_per_cta < Ns) ? s_begin + rows_per_cta : Ns;
+
+  for (int64_t tile = s_begin; tile < s_end; tile += SB) {
+    const int nsb = (int)((s_end - tile) < SB ? (s_end - tile) : SB);
+    __syncthreads();  // the previous tile's readers are done
+    for (int i = threadIdx.x; i < nsb * 3; i += BT) {
+      xs_s[i / 3][i % 3] = r_src[tile * 3 + i];
+      if (ND) ns_s[i / 3][i % 3] = n_src[tile * 3 + i];
     }
-    const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
-    const Real rinv = rsqrt_masked<RSQ>(r2);
-    Real u[K0 * K1];
-    if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u, dx, rinv, n, r2, mu);
-    else PairMatrix<KID, Real>::run(u, dx, rinv, n);
-    if (K1 == 1) {
-      // one entry per (row, target): the direct store is already coalesced
-      if (t < Nt) {
+    __syncthreads();
+#pragma unroll 2
+    for (int si = 0; si < nsb; si++) {
+      const int64_t s = tile + si;
+      const Real xs[3] = {xs_s[si][0], xs_s[si][1], xs_s[si][2]};
+      Real n[3] = {0, 0, 0};
+      if (ND) {
 #pragma unroll
-        for (int k0 = 0; k0 < K0; k0++) M[(s * K0 + k0) * ldM + t] = u[k0] * scale;
+        for (int k = 0; k < 3; k++) n[k] = ns_s[si][k];
       }
-    } else {
-      __syncthreads();  // previous row's readers are done
+      Real u[T][K0 * K1];
 #pragma unroll
-      for (int k0 = 0; k0 < K0; k0++)
+      for (int j = 0; j < T; j++) {
+        const Real dx[3] = {xt[j][0] - xs[0], xt[j][1] - xs[1], xt[j][2] - xs[2]};
+        const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
+        const Real rinv = rsqrt_masked<RSQ>(r2);
+        if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u[j], dx, rinv, n, r2, mu);
+        else PairMatrix<KID, Real>::run(u[j], dx, rinv, n);
 #pragma unroll
-        for (int k1 = 0; k1 < K1; k1++) stage[k0][threadIdx.x * K1 + k1] = u[k0 * K1 + k1] * scale;
-      __syncthreads();
+        for (int k = 0; k < K0 * K1; k++) u[j][k] *= scale;
+      }
+      if constexpr (DIRECT) {
+        // T == V consecutive targets of a row: one vector per (thread, row) straight from registers
 #pragma unroll
-      for (int k0 = 0; k0 < K0; k0++) {
-        Real* row = M + (s * K0 + k0) * ldM + t_blk * K1;
-        for (int c = threadIdx.x; c < nt_blk * K1; c += BT) row[c] = stage[k0][c];
+        for (int k0 = 0; k0 < K0; k0++) {
+          Real* p = M + (s * K0 + k0) * ldM + t0;
+          if (t0 + T <= Nt) {
+            Real v[V];
+#pragma unroll
+            for (int j = 0; j < V; j++) v[j] = u[j][k0];
+            *reinterpret_cast<Vec*>(p) = *reinterpret_cast<const Vec*>(v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < T; j++)
+              if (t0 + j < Nt) p[j] = u[j][k0];
+          }
+        }
+      } else {
+        // Row k0's segment starts at M + (s*K0+k0)*ldM + t_blk*K1; `mis` elements precede its first 16-byte boundary.
+        // Column c is staged at index c + pad with pad = (V - mis) % V, so columns mis, mis+V, ... sit on 16-byte
+        // boundaries on both sides.
+        int mis[K0];
+#pragma unroll
+        for (int k0 = 0; k0 < K0; k0++) {
+          const uintptr_t a = (uintptr_t)(M + (s * K0 + k0) * ldM + t_blk * K1) / sizeof(Real);
+          mis[k0] = (int)((V - a % V) % V);
+        }
+        __syncthreads();  // the previous row's readers are done
+#pragma unroll
+        for (int k0 = 0; k0 < K0; k0++) {
+          Real* st = &stage[k0][(V - mis[k0]) % V + threadIdx.x * (T * K1)];
+#pragma unroll
+          for (int j = 0; j < T; j++)
+#pragma unroll
+            for (int k1 = 0; k1 < K1; k1++) st[j * K1 + k1] = u[j][k0 * K1 + k1];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k0 = 0; k0 < K0; k0++) {
+          Real* row = M + (s * K0 + k0) * ldM + t_blk * K1;
+          const int pad = (V - mis[k0]) % V;
+          const int head = mis[k0] < n_col ? mis[k0] : n_col;
+          const int n_vec = (n_col - head) / V;
+          const int tail0 = head + n_vec * V;
+          if ((int)threadIdx.x < head) row[threadIdx.x] = stage[k0][pad + threadIdx.x];
+          for (int i = threadIdx.x; i < n_vec; i += BT)
+            *reinterpret_cast<Vec*>(row + head + i * V) = *reinterpret_cast<const Vec*>(&stage[k0][pad + head + i * V]);
+          if (tail0 + (int)threadIdx.x < n_col) row[tail0 + threadIdx.x] = stage[k0][pad + tail0 + threadIdx.x];
+        }
       }
     }
   }

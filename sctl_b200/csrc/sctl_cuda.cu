@@ -626,28 +626,43 @@ int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, in
 // ---------------------------------------------------------------------------------------------
 // KernelMatrix
 // ---------------------------------------------------------------------------------------------
-template <class Real, int KID>
-int kmat_device_k(int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
-  constexpr int BT = 128;
-  // a CTA keeps its BT targets in registers and walks sources s = blockIdx.y, blockIdx.y + gridDim.y, ...; enough
-  // CTAs to fill the machine (~32 per SM), few enough that each one amortises its target loads over many rows
-  const int64_t n_tb = (Nt + BT - 1) / BT;
-  const int64_t rows = std::max<int64_t>(1, std::min<int64_t>(Ns, (148 * 32 + n_tb - 1) / n_tb));
-  dim3 grid((unsigned)n_tb, (unsigned)std::min<int64_t>(rows, 65535));
+template <class Real, int KID, bool DIRECT>
+int kmat_launch(int rsq, dim3 grid, int64_t Ns, int64_t Nt, int64_t rows_per_cta, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
   const Real scale = scale_factor<Real>(KID);
-  switch (rsq_mode_for_digits<Real>(digits)) {
-    case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
-    case RSQ_NEWTON: kernel_matrix_kernel<Real, KID, RSQ_NEWTON, BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
-    default: kernel_matrix_kernel<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON), BT><<<grid, BT, 0, stream>>>(Ns, Nt, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+  switch (rsq) {
+    case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, DIRECT><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+    case RSQ_NEWTON: kernel_matrix_kernel<Real, KID, RSQ_NEWTON, DIRECT><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+    default: kernel_matrix_kernel<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON), DIRECT><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
   }
   CU_TRY(cudaGetLastError());
   return 0;
 }
 
+template <class Real, int KID>
+int kmat_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
+  constexpr int T = KmatShape<Real, KID>::T, V = KmatShape<Real, KID>::V;
+  // A CTA keeps its KMAT_BT * T targets in registers and walks a contiguous range of source rows.  Enough CTAs for four
+  // full waves of the machine (16 CTAs of 128 threads per SM) when the matrix is that large, so that the last wave is
+  // short against the whole; never fewer CTAs than one per (target block, row) allows -- small blocks (hundreds x
+  // hundreds, boundary_integral.txx:1191-1211) are latency-bound and want every row on its own CTA.
+  const int64_t n_tb = (Nt + KMAT_BT * T - 1) / (KMAT_BT * T);
+  if (n_tb > 2147483647LL) return fail("too many target blocks");
+  const int64_t want_y = std::max<int64_t>(1, ((int64_t)g.dev[dev].sms * 64 + n_tb - 1) / n_tb);
+  const int64_t gy0 = std::min<int64_t>({Ns, want_y, 65535});
+  const int64_t rows_per_cta = (Ns + gy0 - 1) / gy0;
+  dim3 grid((unsigned)n_tb, (unsigned)((Ns + rows_per_cta - 1) / rows_per_cta));
+  const int rsq = rsq_mode_for_digits<Real>(digits);
+  if constexpr (KerTraits<KID>::K1 == 1) {
+    // rows 16-byte aligned at every thread's first column: vectors go straight from registers to M
+    if ((uintptr_t)M % 16 == 0 && ldM % V == 0) return kmat_launch<Real, KID, true>(rsq, grid, Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+  }
+  return kmat_launch<Real, KID, false>(rsq, grid, Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+}
+
 template <class Real>
-int kmat_device_r(int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, double ctx0, cudaStream_t stream) {
+int kmat_device_r(int dev, int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, double ctx0, cudaStream_t stream) {
 #define SCTL_CUDA_CASE(K) \
-  case K: return kmat_device_k<Real, K>(digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)r_trg, (Real*)M, ldM, (Real)ctx0, stream);
+  case K: return kmat_device_k<Real, K>(dev, digits, Ns, Nt, (const Real*)r_src, (const Real*)n_src, (const Real*)r_trg, (Real*)M, ldM, (Real)ctx0, stream);
   switch (kid) {
     SCTL_CUDA_CASE(LAPLACE3D_FXU)
     SCTL_CUDA_CASE(LAPLACE3D_DXU)
@@ -670,14 +685,14 @@ int kmat_device_r(int kid, int digits, int64_t Ns, int64_t Nt, const void* r_src
 #undef SCTL_CUDA_CASE
 }
 
-int kmat_device_any(int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, double ctx0, cudaStream_t stream) {
+int kmat_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* r_trg, void* M, int64_t ldM, double ctx0, cudaStream_t stream) {
   const KernelInfo ki = kernel_info(kid);
   if (Ns == 0 || Nt == 0) return 0;
   if (!r_src || !r_trg || !M) return fail("null array pointer");
   if (ki.nd && !n_src) return fail("kernel %s needs source normals (n_src is NULL)", ki.name);
   if (ldM < Nt * ki.k1) return fail("ldM (%lld) smaller than Nt*K1 (%lld)", (long long)ldM, (long long)(Nt * ki.k1));
-  if (real_bytes == 8) return kmat_device_r<double>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, ctx0, stream);
-  return kmat_device_r<float>(kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+  if (real_bytes == 8) return kmat_device_r<double>(dev, kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+  return kmat_device_r<float>(dev, kid, digits, Ns, Nt, r_src, n_src, r_trg, M, ldM, ctx0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1078,7 +1093,7 @@ int sctl_cuda_kernel_matrix_device(int kernel_id, int real_bytes, int digits, in
   if (decode_ctx(kernel_id, real_bytes, ctx, ctx_bytes, &ctx0)) return 1;
   int dev;
   if (current_device_ready(&dev)) return 1;
-  return kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_r_trg, d_M, ldM, ctx0, (cudaStream_t)stream);
+  return kmat_device_any(dev, kernel_id, real_bytes, digits, Ns, Nt, d_r_src, d_n_src, d_r_trg, d_M, ldM, ctx0, (cudaStream_t)stream);
 }
 
 int sctl_cuda_eval(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt, const void* r_src, const void* n_src, const void* v_src,
@@ -1162,7 +1177,7 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
       if (b_ns) memcpy(h + o_ns, n_src, b_ns);
       memcpy(h + o_rt, r_trg, b_rt);
       CU_TRY(cudaMemcpyAsync(d, h, o_M, cudaMemcpyHostToDevice, st));
-      if (kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d + o_rs, b_ns ? d + o_ns : nullptr, d + o_rt, d + o_M, cols, ctx0, st)) return 1;
+      if (kmat_device_any(dev, kernel_id, real_bytes, digits, Ns, Nt, d + o_rs, b_ns ? d + o_ns : nullptr, d + o_rt, d + o_M, cols, ctx0, st)) return 1;
       CU_TRY(cudaMemcpyAsync(h + o_M, d + o_M, b_M, cudaMemcpyDeviceToHost, st));
       CU_TRY(cudaStreamSynchronize(st));
       if (ldM == cols) memcpy(M, h + o_M, b_M);
@@ -1177,7 +1192,7 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
   CU_TRY(cudaMemcpyAsync(d_rs.p, r_src, rb * Ns * 3, cudaMemcpyHostToDevice, st));
   if (ki.nd) CU_TRY(cudaMemcpyAsync(d_ns.p, n_src, rb * Ns * ki.nd, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(d_rt.p, r_trg, rb * Nt * 3, cudaMemcpyHostToDevice, st));
-  if (kmat_device_any(kernel_id, real_bytes, digits, Ns, Nt, d_rs.p, d_ns.p, d_rt.p, d_M.p, cols, ctx0, st)) return 1;
+  if (kmat_device_any(dev, kernel_id, real_bytes, digits, Ns, Nt, d_rs.p, d_ns.p, d_rt.p, d_M.p, cols, ctx0, st)) return 1;
   CU_TRY(cudaMemcpy2DAsync(M, rb * ldM, d_M.p, rb * cols, rb * cols, rows, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   return 0;

@@ -219,6 +219,69 @@ def test_device_path_unaligned_views_and_streams(sb, cpu_oracle, dtype):
         assert np.all(Mh[:, Ntm * k1:] == -7.0)  # padding columns untouched
 
 
+# KernelMatrix shapes around the kernel's internal boundaries (csrc/kmat_kernel.cuh): 128 threads x T targets per CTA
+# (T = 1, 2 or 4: segments of 128 / 256 / 512 targets), 32-row source tiles, vector stores with scalar head and tail
+KMAT_SHAPES = [(1, 1), (2, 3), (33, 127), (31, 129), (5, 255), (7, 257), (65, 511), (3, 513), (40, 1030)]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_kernel_matrix_device_over_shapes_pitches_and_alignments(sb, cpu_oracle, kernel, dtype):
+    """Every store of the KernelMatrix kernel is a 16-byte vector where the row allows it: cover row pitches that keep
+    every row aligned, that misalign every other row (FP64) or three rows in four (FP32), and a matrix that starts 1..3
+    elements past an aligned address; padding columns and the elements in front of the view must stay untouched."""
+    import torch
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    tdt = torch.float64 if dtype is np.float64 else torch.float32
+    for case, (Ns, Nt) in enumerate(KMAT_SHAPES):
+        r_src, n_src, _, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
+        want = cpu_oracle.kernel_matrix(kernel, r_src, n_src, r_trg, dtype=dtype)
+        d_rs, d_rt = torch.from_numpy(r_src).cuda(), torch.from_numpy(r_trg).cuda()
+        d_ns = torch.from_numpy(n_src).cuda() if nd else None
+        cols = Nt * k1
+        for pad, off in ((0, 0), (1, 0), ((-cols) % 4, 0), ((-cols) % 4 + 2, 1), (3, 3)):
+            ld = cols + pad
+            buf = torch.full((off + Ns * k0 * ld,), -7.0, dtype=tdt, device="cuda")
+            dM = buf[off:].view(Ns * k0, ld)
+            sb.kernel_matrix_device(sb.KERNELS[kernel], d_rs, d_ns, d_rt, dM, ldM=ld)
+            torch.cuda.synchronize()
+            Mh = dM.cpu().numpy()
+            err = rel_err(Mh[:, :cols], want)
+            assert err <= TOL[dtype] * (10 if dtype == np.float32 else 1), (kernel, dtype.__name__, Ns, Nt, pad, off, err)
+            assert np.all(Mh[:, cols:] == -7.0) and np.all(buf[:off].cpu().numpy() == -7.0), (kernel, Ns, Nt, pad, off)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("kernel", ["Laplace3D_FxU", "Laplace3D_DxU", "Stokes3D_FxU"])
+def test_kernel_matrix_device_large_rows_spot_checked(sb, cpu_oracle, kernel, dtype):
+    """A matrix large enough that a CTA walks several 32-row source tiles (rows per CTA = Ns * target blocks / (64 CTAs per
+    SM); 0.8 - 1.6 GB written): 48 rows spread over the row range against the oracle, and every entry written (the
+    buffer is pre-filled with NaN).  Aligned and odd row pitch."""
+    import torch
+    from sctl_b200 import synth
+    k0, k1, nd = cases.KERNELS[kernel]
+    tdt = torch.float64 if dtype is np.float64 else torch.float32
+    Ns, Nt = (20000, 10239) if k1 == 1 else (16000, 3413)
+    r_src, n_src, _, r_trg = synth.cube(Ns, Nt, k0, nd, dtype=dtype)
+    d_rs, d_rt = torch.from_numpy(r_src).cuda(), torch.from_numpy(r_trg).cuda()
+    d_ns = torch.from_numpy(n_src).cuda() if nd else None
+    sel = np.unique(np.concatenate([np.arange(0, Ns, Ns // 40), [31, 32, 33, Ns - 33, Ns - 2, Ns - 1]]))
+    want = cpu_oracle.kernel_matrix(kernel, r_src.reshape(-1, 3)[sel].reshape(-1), None if n_src is None else n_src.reshape(-1, 3)[sel].reshape(-1), r_trg, dtype=dtype)
+    cols = Nt * k1
+    for ld in (cols + (-cols) % 4, cols + (-cols) % 4 + 1):
+        dM = torch.full((Ns * k0, ld), float("nan"), dtype=tdt, device="cuda")
+        sb.kernel_matrix_device(sb.KERNELS[kernel], d_rs, d_ns, d_rt, dM, ldM=ld)
+        torch.cuda.synchronize()
+        assert not bool(torch.isnan(dM[:, :cols]).any()), (kernel, ld)
+        assert bool(torch.isnan(dM[:, cols:]).all()), (kernel, ld)
+        rows = (sel[:, None] * k0 + np.arange(k0)[None, :]).reshape(-1)
+        got = dM[torch.from_numpy(rows).cuda()][:, :cols].cpu().numpy()
+        err = rel_err(got, want)
+        assert err <= TOL[dtype] * (10 if dtype == np.float32 else 1), (kernel, dtype.__name__, ld, err)
+        del dM
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 def test_eval_equals_kernel_matrix_apply_and_linearity(sb, kernel):
     from sctl_b200 import synth
