@@ -31,22 +31,28 @@ template <> struct KmatVec<float> { using type = float4; };
 
 // Targets per thread: K1 == 1 -> one 16-byte vector of consecutive targets; K1 > 1 -> 8 bytes' worth of targets (the
 // staging buffer holds K0 * BT * T * K1 Reals: 27 KB for the K0 x K1 = 3 x 9 kernels in either precision).
-template <class Real, int KID> struct KmatShape {
+// Rows per round R: the source rows a thread computes before it stores.  DIRECT: 2 (independent pairs in flight).  Staged:
+// every round costs two CTA barriers, so the cheap K1 == 1 kernels (13..19 instructions per pair) take 4 rows per
+// round; K1 > 1 kernels do enough work per row (and their stage is K0 rows already).
+template <class Real, int KID, bool DIRECT> struct KmatShape {
   static constexpr int V = 16 / (int)sizeof(Real);
   static constexpr int T = KerTraits<KID>::K1 == 1 ? V : 8 / (int)sizeof(Real);
+  static constexpr int R = DIRECT ? 2 : (KerTraits<KID>::K1 == 1 ? 4 : 1);
 };
 
 template <class Real, int KID, int RSQ, bool DIRECT>
 __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int64_t Nt, int64_t rows_per_cta, const Real* __restrict__ r_src, const Real* __restrict__ n_src,
                                                               const Real* __restrict__ r_trg, Real* __restrict__ M, int64_t ldM, Real scale, Real mu) {
   constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
-  constexpr int BT = KMAT_BT, SB = KMAT_SRC_TILE, V = KmatShape<Real, KID>::V, T = KmatShape<Real, KID>::T;
+  using Shape = KmatShape<Real, KID, DIRECT>;
+  constexpr int BT = KMAT_BT, SB = KMAT_SRC_TILE, V = Shape::V, T = Shape::T, R = Shape::R;
   constexpr int W = BT * T * K1;  // columns of a row segment
   using Vec = typename KmatVec<Real>::type;
+  static_assert(!DIRECT || (K1 == 1 && T == V), "the direct path stores one vector of consecutive targets per row");
+  static_assert(SB % R == 0, "a source tile is a whole number of rounds");
   __shared__ Real xs_s[SB][3];
   __shared__ Real ns_s[ND ? SB : 1][3];
-  static_assert(!DIRECT || (K1 == 1 && T == V), "the direct path stores one vector of consecutive targets per row");
-  __shared__ __align__(16) Real stage[DIRECT ? 1 : K0][DIRECT ? V : W + V];
+  __shared__ __align__(16) Real stage[DIRECT ? 1 : R * K0][DIRECT ? V : W + V];
 
   const int64_t t_blk = (int64_t)blockIdx.x * (BT * T);
   const int64_t t0 = t_blk + (int64_t)threadIdx.x * T;
@@ -67,73 +73,76 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
       if (ND) ns_s[i / 3][i % 3] = n_src[tile * 3 + i];
     }
     __syncthreads();
-#pragma unroll 2
-    for (int si = 0; si < nsb; si++) {
-      const int64_t s = tile + si;
-      const Real xs[3] = {xs_s[si][0], xs_s[si][1], xs_s[si][2]};
-      Real n[3] = {0, 0, 0};
-      if (ND) {
+#pragma unroll 1
+    for (int si0 = 0; si0 < nsb; si0 += R) {
+      Real u[R][T][K0 * K1];
 #pragma unroll
-        for (int k = 0; k < 3; k++) n[k] = ns_s[si][k];
+      for (int r = 0; r < R; r++) {
+        const int si = si0 + r < nsb ? si0 + r : nsb - 1;  // a ragged last round recomputes the last row (not stored)
+        const Real xs[3] = {xs_s[si][0], xs_s[si][1], xs_s[si][2]};
+        Real n[3] = {0, 0, 0};
+        if (ND) {
+#pragma unroll
+          for (int k = 0; k < 3; k++) n[k] = ns_s[si][k];
+        }
+#pragma unroll
+        for (int j = 0; j < T; j++) {
+          const Real dx[3] = {xt[j][0] - xs[0], xt[j][1] - xs[1], xt[j][2] - xs[2]};
+          const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
+          const Real rinv = rsqrt_masked<RSQ>(r2);
+          if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u[r][j], dx, rinv, n, r2, mu);
+          else PairMatrix<KID, Real>::run(u[r][j], dx, rinv, n);
+#pragma unroll
+          for (int k = 0; k < K0 * K1; k++) u[r][j][k] *= scale;
+        }
       }
-      Real u[T][K0 * K1];
-#pragma unroll
-      for (int j = 0; j < T; j++) {
-        const Real dx[3] = {xt[j][0] - xs[0], xt[j][1] - xs[1], xt[j][2] - xs[2]};
-        const Real r2 = fma(dx[2], dx[2], fma(dx[1], dx[1], dx[0] * dx[0]));
-        const Real rinv = rsqrt_masked<RSQ>(r2);
-        if constexpr (KerNeedsCtx<KID>::value) PairMatrix<KID, Real>::run_ctx(u[j], dx, rinv, n, r2, mu);
-        else PairMatrix<KID, Real>::run(u[j], dx, rinv, n);
-#pragma unroll
-        for (int k = 0; k < K0 * K1; k++) u[j][k] *= scale;
-      }
+      const int n_rows = ((nsb - si0) < R ? (nsb - si0) : R) * K0;  // matrix rows of this round
+      const int64_t row0 = (tile + si0) * K0;
       if constexpr (DIRECT) {
         // T == V consecutive targets of a row: one vector per (thread, row) straight from registers
 #pragma unroll
-        for (int k0 = 0; k0 < K0; k0++) {
-          Real* p = M + (s * K0 + k0) * ldM + t0;
-          if (t0 + T <= Nt) {
-            Real v[V];
+        for (int rr = 0; rr < R * K0; rr++) {
+          if (rr < n_rows) {
+            Real* p = M + (row0 + rr) * ldM + t0;
+            if (t0 + T <= Nt) {
+              Real v[V];
 #pragma unroll
-            for (int j = 0; j < V; j++) v[j] = u[j][k0];
-            *reinterpret_cast<Vec*>(p) = *reinterpret_cast<const Vec*>(v);
-          } else {
+              for (int j = 0; j < V; j++) v[j] = u[rr / K0][j][rr % K0];
+              *reinterpret_cast<Vec*>(p) = *reinterpret_cast<const Vec*>(v);
+            } else {
 #pragma unroll
-            for (int j = 0; j < T; j++)
-              if (t0 + j < Nt) p[j] = u[j][k0];
+              for (int j = 0; j < T; j++)
+                if (t0 + j < Nt) p[j] = u[rr / K0][j][rr % K0];
+            }
           }
         }
       } else {
-        // Row k0's segment starts at M + (s*K0+k0)*ldM + t_blk*K1; `mis` elements precede its first 16-byte boundary.
-        // Column c is staged at index c + pad with pad = (V - mis) % V, so columns mis, mis+V, ... sit on 16-byte
-        // boundaries on both sides.
-        int mis[K0];
+        // Matrix row `row`'s segment starts at M + row*ldM + t_blk*K1, `pad` elements past a 16-byte boundary.  Column
+        // c is staged at index pad + c: the stage rows are 16-byte aligned, so global and shared addresses of a column
+        // are congruent modulo 16 and the columns from mis = (V - pad) % V on move as aligned vectors on both sides.
+        __syncthreads();  // the previous round's readers are done
 #pragma unroll
-        for (int k0 = 0; k0 < K0; k0++) {
-          const uintptr_t a = (uintptr_t)(M + (s * K0 + k0) * ldM + t_blk * K1) / sizeof(Real);
-          mis[k0] = (int)((V - a % V) % V);
-        }
-        __syncthreads();  // the previous row's readers are done
-#pragma unroll
-        for (int k0 = 0; k0 < K0; k0++) {
-          Real* st = &stage[k0][(V - mis[k0]) % V + threadIdx.x * (T * K1)];
+        for (int rr = 0; rr < R * K0; rr++) {
+          const int pad = (int)(((uintptr_t)(M + (row0 + rr) * ldM + t_blk * K1) / sizeof(Real)) % V);
+          Real* st = &stage[rr][pad + threadIdx.x * (T * K1)];
 #pragma unroll
           for (int j = 0; j < T; j++)
 #pragma unroll
-            for (int k1 = 0; k1 < K1; k1++) st[j * K1 + k1] = u[j][k0 * K1 + k1];
+            for (int k1 = 0; k1 < K1; k1++) st[j * K1 + k1] = u[rr / K0][j][(rr % K0) * K1 + k1];
         }
         __syncthreads();
-#pragma unroll
-        for (int k0 = 0; k0 < K0; k0++) {
-          Real* row = M + (s * K0 + k0) * ldM + t_blk * K1;
-          const int pad = (V - mis[k0]) % V;
-          const int head = mis[k0] < n_col ? mis[k0] : n_col;
+#pragma unroll 1
+        for (int rr = 0; rr < n_rows; rr++) {
+          Real* row = M + (row0 + rr) * ldM + t_blk * K1;
+          const int pad = (int)(((uintptr_t)row / sizeof(Real)) % V);
+          const int mis = (V - pad) % V;
+          const int head = mis < n_col ? mis : n_col;
           const int n_vec = (n_col - head) / V;
           const int tail0 = head + n_vec * V;
-          if ((int)threadIdx.x < head) row[threadIdx.x] = stage[k0][pad + threadIdx.x];
-          for (int i = threadIdx.x; i < n_vec; i += BT)
-            *reinterpret_cast<Vec*>(row + head + i * V) = *reinterpret_cast<const Vec*>(&stage[k0][pad + head + i * V]);
-          if (tail0 + (int)threadIdx.x < n_col) row[tail0 + threadIdx.x] = stage[k0][pad + tail0 + threadIdx.x];
+          const Real* st = &stage[rr][pad];
+          if ((int)threadIdx.x < head) row[threadIdx.x] = st[threadIdx.x];
+          for (int i = threadIdx.x; i < n_vec; i += BT) *reinterpret_cast<Vec*>(row + head + i * V) = *reinterpret_cast<const Vec*>(st + head + i * V);
+          if (tail0 + (int)threadIdx.x < n_col) row[tail0 + threadIdx.x] = st[tail0 + threadIdx.x];
         }
       }
     }

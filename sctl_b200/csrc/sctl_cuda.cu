@@ -640,7 +640,7 @@ int kmat_launch(int rsq, dim3 grid, int64_t Ns, int64_t Nt, int64_t rows_per_cta
 
 template <class Real, int KID>
 int kmat_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
-  constexpr int T = KmatShape<Real, KID>::T, V = KmatShape<Real, KID>::V;
+  constexpr int T = KmatShape<Real, KID, false>::T, V = KmatShape<Real, KID, false>::V;  // the same for both paths
   // A CTA keeps its KMAT_BT * T targets in registers and walks a contiguous range of source rows.  Enough CTAs for four
   // full waves of the machine (16 CTAs of 128 threads per SM) when the matrix is that large, so that the last wave is
   // short against the whole; never fewer CTAs than one per (target block, row) allows -- small blocks (hundreds x
