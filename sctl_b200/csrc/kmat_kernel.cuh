@@ -7,9 +7,12 @@
 //   * every global store is a 16-byte vector.  DIRECT (K1 == 1, M and the row pitch 16-byte aligned; chosen by the
 //     host): a thread's T = 16/sizeof(Real) consecutive targets are one vector, stored straight from registers (a warp
 //     writes 512 contiguous bytes per instruction).  Otherwise the K0 x (T*K1) values of a thread are staged through
-//     shared memory and the row segments are written out as aligned vectors, scalar elements only before the first and
-//     after the last 16-byte boundary of a segment -- rows need not be 16-byte aligned (odd ldM, matrix views), the
-//     staging index is shifted per row so that the shared-memory side of every vector is aligned too;
+//     shared memory, WARP by warp: a warp owns the 32*T*K1 contiguous columns of its lanes' targets, stages them in its
+//     own slice of shared memory and writes them out itself as aligned vectors, scalar elements only before the first
+//     and after the last 16-byte boundary of its segment -- rows need not be 16-byte aligned (odd ldM, matrix views),
+//     the staging index is shifted per row so that the shared-memory side of every vector is aligned too.  Only
+//     __syncwarp() orders the two phases: the row loop has no CTA barrier, so warps that are computing (the Helmholtz
+//     kernels spend ~70 FP64 instructions per pair) never wait for warps that are storing;
 //   * source coordinates (and normals) of a tile of rows are brought into shared memory by the whole CTA before the
 //     tile's rows are computed, so the row loop has no global load in it (round 1's kernel loaded them per row and
 //     spent its time on the long scoreboard: profiles/r1_ncu_kernel_matrix.md, 62 % / 40 % of the HBM copy bandwidth
@@ -30,10 +33,10 @@ template <> struct KmatVec<double> { using type = double2; };
 template <> struct KmatVec<float> { using type = float4; };
 
 // Targets per thread: K1 == 1 -> one 16-byte vector of consecutive targets; K1 > 1 -> 8 bytes' worth of targets (the
-// staging buffer holds K0 * BT * T * K1 Reals: 27 KB for the K0 x K1 = 3 x 9 kernels in either precision).
+// staging buffer holds R * K0 * BT * T * K1 Reals: 27 KB for the K0 x K1 = 3 x 9 kernels in either precision).
 // Rows per round R: the source rows a thread computes before it stores.  DIRECT: 2 (independent pairs in flight).  Staged:
-// every round costs two CTA barriers, so the cheap K1 == 1 kernels (13..19 instructions per pair) take 4 rows per
-// round; K1 > 1 kernels do enough work per row (and their stage is K0 rows already).
+// the cheap K1 == 1 kernels (13..19 instructions per pair) take 4 rows per round so that the round's address
+// arithmetic and its two __syncwarp() are spread over more pairs; K1 > 1 kernels do enough work per row.
 template <class Real, int KID, bool DIRECT> struct KmatShape {
   static constexpr int V = 16 / (int)sizeof(Real);
   static constexpr int T = KerTraits<KID>::K1 == 1 ? V : 8 / (int)sizeof(Real);
@@ -46,13 +49,13 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
   constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
   using Shape = KmatShape<Real, KID, DIRECT>;
   constexpr int BT = KMAT_BT, SB = KMAT_SRC_TILE, V = Shape::V, T = Shape::T, R = Shape::R;
-  constexpr int W = BT * T * K1;  // columns of a row segment
   using Vec = typename KmatVec<Real>::type;
   static_assert(!DIRECT || (K1 == 1 && T == V), "the direct path stores one vector of consecutive targets per row");
   static_assert(SB % R == 0, "a source tile is a whole number of rounds");
+  constexpr int WW = 32 * T * K1;  // columns of a warp's part of the segment
   __shared__ Real xs_s[SB][3];
   __shared__ Real ns_s[ND ? SB : 1][3];
-  __shared__ __align__(16) Real stage[DIRECT ? 1 : R * K0][DIRECT ? V : W + V];
+  __shared__ __align__(16) Real stage[DIRECT ? 1 : BT / 32][DIRECT ? 1 : R * K0][DIRECT ? V : WW + V];
 
   const int64_t t_blk = (int64_t)blockIdx.x * (BT * T);
   const int64_t t0 = t_blk + (int64_t)threadIdx.x * T;
@@ -61,7 +64,10 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
   for (int j = 0; j < T; j++)
 #pragma unroll
     for (int k = 0; k < 3; k++) xt[j][k] = (t0 + j < Nt) ? r_trg[(t0 + j) * 3 + k] : (Real)0;
-  const int n_col = (int)(((Nt - t_blk) < BT * T ? (Nt - t_blk) : BT * T) * K1);  // valid columns of this CTA's segments
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t c_warp = t_blk * K1 + (int64_t)warp * WW;  // first column of this warp's part
+  const int64_t left = Nt * K1 - c_warp;
+  const int n_col = (int)(left < 0 ? 0 : (left < WW ? left : WW));  // valid columns of this warp's part
   const int64_t s_begin = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t s_end = (s_begin + rows_per_cta < Ns) ? s_begin + rows_per_cta : Ns;
 
@@ -73,7 +79,8 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
       if (ND) ns_s[i / 3][i % 3] = n_src[tile * 3 + i];
     }
     __syncthreads();
-#pragma unroll 1
+    if (n_col == 0) continue;  // (warp-uniform; no barrier below) nothing of this warp's part lies inside the matrix
+#pragma unroll(R == 1 ? 2 : 1)
     for (int si0 = 0; si0 < nsb; si0 += R) {
       Real u[R][T][K0 * K1];
 #pragma unroll
@@ -117,32 +124,35 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
           }
         }
       } else {
-        // Matrix row `row`'s segment starts at M + row*ldM + t_blk*K1, `pad` elements past a 16-byte boundary.  Column
-        // c is staged at index pad + c: the stage rows are 16-byte aligned, so global and shared addresses of a column
-        // are congruent modulo 16 and the columns from mis = (V - pad) % V on move as aligned vectors on both sides.
-        __syncthreads();  // the previous round's readers are done
+        // This warp's part of matrix row `row` starts at M + row*ldM + c_warp, `pad` elements past a 16-byte boundary.
+        // Column c of the part is staged at index pad + c: the stage rows are 16-byte aligned, so global and shared
+        // addresses of a column are congruent modulo 16 and the columns from mis = (V - pad) % V on move as aligned
+        // vectors on both sides.
+        __syncwarp();  // this warp's reads of the previous round are done
 #pragma unroll
         for (int rr = 0; rr < R * K0; rr++) {
-          const int pad = (int)(((uintptr_t)(M + (row0 + rr) * ldM + t_blk * K1) / sizeof(Real)) % V);
-          Real* st = &stage[rr][pad + threadIdx.x * (T * K1)];
+          const int pad = (int)(((uintptr_t)(M + (row0 + rr) * ldM + c_warp) / sizeof(Real)) % V);
+          Real* st = &stage[warp][rr][pad + lane * (T * K1)];
 #pragma unroll
           for (int j = 0; j < T; j++)
 #pragma unroll
             for (int k1 = 0; k1 < K1; k1++) st[j * K1 + k1] = u[rr / K0][j][(rr % K0) * K1 + k1];
         }
-        __syncthreads();
-#pragma unroll 1
-        for (int rr = 0; rr < n_rows; rr++) {
-          Real* row = M + (row0 + rr) * ldM + t_blk * K1;
-          const int pad = (int)(((uintptr_t)row / sizeof(Real)) % V);
-          const int mis = (V - pad) % V;
-          const int head = mis < n_col ? mis : n_col;
-          const int n_vec = (n_col - head) / V;
-          const int tail0 = head + n_vec * V;
-          const Real* st = &stage[rr][pad];
-          if ((int)threadIdx.x < head) row[threadIdx.x] = st[threadIdx.x];
-          for (int i = threadIdx.x; i < n_vec; i += BT) *reinterpret_cast<Vec*>(row + head + i * V) = *reinterpret_cast<const Vec*>(st + head + i * V);
-          if (tail0 + (int)threadIdx.x < n_col) row[tail0 + threadIdx.x] = st[tail0 + threadIdx.x];
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < R * K0; rr++) {
+          if (rr < n_rows) {
+            Real* row = M + (row0 + rr) * ldM + c_warp;
+            const int pad = (int)(((uintptr_t)row / sizeof(Real)) % V);
+            const int mis = (V - pad) % V;
+            const int head = mis < n_col ? mis : n_col;
+            const int n_vec = (n_col - head) / V;
+            const int tail0 = head + n_vec * V;
+            const Real* st = &stage[warp][rr][pad];
+            if (lane < head) row[lane] = st[lane];
+            for (int i = lane; i < n_vec; i += 32) *reinterpret_cast<Vec*>(row + head + i * V) = *reinterpret_cast<const Vec*>(st + head + i * V);
+            if (tail0 + lane < n_col) row[tail0 + lane] = st[tail0 + lane];
+          }
         }
       }
     }
