@@ -68,6 +68,12 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
   const int64_t c_warp = t_blk * K1 + (int64_t)warp * WW;  // first column of this warp's part
   const int64_t left = Nt * K1 - c_warp;
   const int n_col = (int)(left < 0 ? 0 : (left < WW ? left : WW));  // valid columns of this warp's part
+  // staged path: alignment of this warp's part.  a0 = elements between the last 16-byte boundary and the part's first
+  // column in matrix row 0, lmod = ldM mod V; `simple`: all rows of the part aligned and the part full
+  constexpr int NV = WW / V;  // vectors per full part
+  const int a0 = (int)(((uintptr_t)(M + c_warp) / sizeof(Real)) & (V - 1));
+  const int lmod = (int)(ldM & (V - 1));
+  const bool simple = a0 == 0 && lmod == 0 && n_col == WW;
   const int64_t s_begin = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t s_end = (s_begin + rows_per_cta < Ns) ? s_begin + rows_per_cta : Ns;
 
@@ -124,34 +130,62 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
           }
         }
       } else {
-        // This warp's part of matrix row `row` starts at M + row*ldM + c_warp, `pad` elements past a 16-byte boundary.
-        // Column c of the part is staged at index pad + c: the stage rows are 16-byte aligned, so global and shared
-        // addresses of a column are congruent modulo 16 and the columns from mis = (V - pad) % V on move as aligned
-        // vectors on both sides.
+        // This warp's part of matrix row `row` starts at wrow = M + row*ldM + c_warp, `pad` elements past a 16-byte
+        // boundary.  Column c of the part is staged at index pad + c: the stage rows are 16-byte aligned, so global and
+        // shared addresses of a column are congruent modulo 16 and the columns from mis = (V - pad) % V on move as
+        // aligned vectors on both sides.  pad = (a0 + row * ldM) mod V needs only the low bits of its terms.
+        Real* wrow = M + row0 * ldM + c_warp;
         __syncwarp();  // this warp's reads of the previous round are done
+        if (simple) {
+          // every row of the part starts on a 16-byte boundary and the part is full: vectors only, no index arithmetic
 #pragma unroll
-        for (int rr = 0; rr < R * K0; rr++) {
-          const int pad = (int)(((uintptr_t)(M + (row0 + rr) * ldM + c_warp) / sizeof(Real)) % V);
-          Real* st = &stage[warp][rr][pad + lane * (T * K1)];
+          for (int rr = 0; rr < R * K0; rr++) {
+            Real* st = &stage[warp][rr][lane * (T * K1)];
 #pragma unroll
-          for (int j = 0; j < T; j++)
+            for (int j = 0; j < T; j++)
 #pragma unroll
-            for (int k1 = 0; k1 < K1; k1++) st[j * K1 + k1] = u[rr / K0][j][(rr % K0) * K1 + k1];
-        }
-        __syncwarp();
+              for (int k1 = 0; k1 < K1; k1++) st[j * K1 + k1] = u[rr / K0][j][(rr % K0) * K1 + k1];
+          }
+          __syncwarp();
 #pragma unroll
-        for (int rr = 0; rr < R * K0; rr++) {
-          if (rr < n_rows) {
-            Real* row = M + (row0 + rr) * ldM + c_warp;
-            const int pad = (int)(((uintptr_t)row / sizeof(Real)) % V);
-            const int mis = (V - pad) % V;
-            const int head = mis < n_col ? mis : n_col;
-            const int n_vec = (n_col - head) / V;
-            const int tail0 = head + n_vec * V;
-            const Real* st = &stage[warp][rr][pad];
-            if (lane < head) row[lane] = st[lane];
-            for (int i = lane; i < n_vec; i += 32) *reinterpret_cast<Vec*>(row + head + i * V) = *reinterpret_cast<const Vec*>(st + head + i * V);
-            if (tail0 + lane < n_col) row[tail0 + lane] = st[tail0 + lane];
+          for (int rr = 0; rr < R * K0; rr++) {
+            if (rr < n_rows) {
+              const Vec* sv = reinterpret_cast<const Vec*>(&stage[warp][rr][0]);
+              Vec* gv = reinterpret_cast<Vec*>(wrow);
+#pragma unroll
+              for (int p = 0; p < (NV + 31) / 32; p++)
+                if (p * 32 + 32 <= NV || lane < NV - p * 32) gv[p * 32 + lane] = sv[p * 32 + lane];
+            }
+            wrow += ldM;
+          }
+        } else {
+          int pads[R * K0];
+#pragma unroll
+          for (int rr = 0; rr < R * K0; rr++) {
+            pads[rr] = (a0 + ((int)(row0 + rr) & (V - 1)) * lmod) & (V - 1);
+            Real* st = &stage[warp][rr][pads[rr] + lane * (T * K1)];
+#pragma unroll
+            for (int j = 0; j < T; j++)
+#pragma unroll
+              for (int k1 = 0; k1 < K1; k1++) st[j * K1 + k1] = u[rr / K0][j][(rr % K0) * K1 + k1];
+          }
+          __syncwarp();
+#pragma unroll
+          for (int rr = 0; rr < R * K0; rr++) {
+            if (rr < n_rows) {
+              const int mis = (V - pads[rr]) & (V - 1);
+              const int head = mis < n_col ? mis : n_col;
+              const int tail0 = head + ((n_col - head) & ~(V - 1));
+              const Real* st = &stage[warp][rr][pads[rr]];
+              if (lane < head) wrow[lane] = st[lane];
+#pragma unroll
+              for (int p = 0; p < (NV + 31) / 32; p++) {
+                const int e = head + (p * 32 + lane) * V;
+                if (e + V <= tail0) *reinterpret_cast<Vec*>(wrow + e) = *reinterpret_cast<const Vec*>(st + e);
+              }
+              if (tail0 + lane < n_col) wrow[tail0 + lane] = st[tail0 + lane];
+            }
+            wrow += ldM;
           }
         }
       }
