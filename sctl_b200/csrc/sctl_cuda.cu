@@ -626,6 +626,9 @@ int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, in
 // ---------------------------------------------------------------------------------------------
 // KernelMatrix
 // ---------------------------------------------------------------------------------------------
+#ifndef SCTL_TUNE_KMAT_CTAS_PER_SM
+#define SCTL_TUNE_KMAT_CTAS_PER_SM 64  // CTAs per SM a large matrix is cut into (tuning builds: tools/ab_build.sh)
+#endif
 template <class Real, int KID, bool DIRECT>
 int kmat_launch(int rsq, dim3 grid, int64_t Ns, int64_t Nt, int64_t rows_per_cta, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
   const Real scale = scale_factor<Real>(KID);
@@ -647,7 +650,7 @@ int kmat_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src
   // hundreds, boundary_integral.txx:1191-1211) are latency-bound and want every row on its own CTA.
   const int64_t n_tb = (Nt + KMAT_BT * T - 1) / (KMAT_BT * T);
   if (n_tb > 2147483647LL) return fail("too many target blocks");
-  const int64_t want_y = std::max<int64_t>(1, ((int64_t)g.dev[dev].sms * 64 + n_tb - 1) / n_tb);
+  const int64_t want_y = std::max<int64_t>(1, ((int64_t)g.dev[dev].sms * SCTL_TUNE_KMAT_CTAS_PER_SM + n_tb - 1) / n_tb);
   const int64_t gy0 = std::min<int64_t>({Ns, want_y, 65535});
   const int64_t rows_per_cta = (Ns + gy0 - 1) / gy0;
   dim3 grid((unsigned)n_tb, (unsigned)((Ns + rows_per_cta - 1) / rows_per_cta));
