@@ -12,6 +12,9 @@ A "step" is one full Eval (all 2^20 targets against all 2^20 sources).
             the work above, D2H of the result, every step.
   roofline  the pair kernel against the FP64 CUDA-core peak measured in this run by a DFMA micro-benchmark
             (MEASURED_PEAKS.json has no FP64 entry); achieved = pairs x F_alg(29 flop) / kernel time.
+            roofline.hbm_view: the same kernel in the contract's HBM form (it is not the binding roof);
+            roofline.kernel_matrix_view (N = 1): the path's HBM-bound kernel, KernelMatrix of the same micro-kernel at
+            8192 x 8192, bytes written / time against MEASURED_PEAKS.json's copy bandwidth, measured after the timed region.
   cpu_baseline  the reference's own OpenMP/AVX Eval (oracle/_ref, the unmodified reference compiled by
             oracle/Makefile; falls back to the C port) on all sources x a strided target subsample, on the box's
             host cores, rank 0, N = 1 only.  The same call provides the parity figure printed in the line.
@@ -144,6 +147,7 @@ def main():
     ap.add_argument("--cpu-targets", type=int, default=1 << 14, help="strided target subsample for the CPU baseline / parity")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-kmat-view", action="store_true", help="skip roofline.kernel_matrix_view (the KernelMatrix write-bandwidth measurement after the timed region)")
     args = ap.parse_args()
 
     # stdout carries exactly one JSON line (rank 0): everything else that libraries print to fd 1 (NCCL's version banner
@@ -344,6 +348,37 @@ def main():
         gbs = traffic * pair_launches / (k_ms * 1e-3) * 1e-9
         roofline["hbm_view"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": traffic, "peak_source": hbm_src,
                                 "note": "targets and v_trg are re-read once per source chunk (%d launches per step); at %.1f %% of the HBM roof the kernel is not memory-bound" % (pair_launches, 100 * gbs / hbm_peak)}
+
+    if world == 1 and not args.no_kmat_view:
+        # The path's one HBM-bound kernel, in the contract's own roofline form: KernelMatrix of the same micro-kernel and
+        # precision (generic-kernel.txx:213-329; csrc/kmat_kernel.cuh), 8192 x 8192 device-resident, 8 launches back to back
+        # per sample, best of 3, CUDA events on the launching stream.  Algorithmic bytes = sizeof(Real)*K0*K1 written per pair.
+        nk = 8192
+        km_rs, km_ns, _, km_rt = synth.cube(nk, nk, k0, nd, dtype=npdt)
+        d_rs, d_rt = torch.from_numpy(km_rs).cuda(), torch.from_numpy(km_rt).cuda()
+        d_ns = torch.from_numpy(km_ns).cuda() if nd else None
+        d_M = torch.empty((nk * k0, nk * k1), dtype=d_rs.dtype, device="cuda")
+        sb.kernel_matrix_device(kernel, d_rs, d_ns, d_rt, d_M)
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(8):
+                sb.kernel_matrix_device(kernel, d_rs, d_ns, d_rt, d_M)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / 8)
+        alg = float(nk) * k0 * nk * k1 * rb
+        hbm_peak, hbm_src = hbm_peak_gbs()
+        gbs = alg / (best * 1e-3) * 1e-9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r2k_ncu_kernel_matrix.md)
+        km_traffic = {("Stokes3D_FxU", 8): 4.775e9, ("Stokes3D_FxU", 4): 2.358e9, ("Laplace3D_FxU", 8): 0.479e9}.get((kernel, rb))
+        roofline["kernel_matrix_view"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": km_traffic,
+                                          "algorithmic_bytes_per_launch": alg, "ms_per_launch": best, "peak_source": hbm_src,
+                                          "kernel": "kernel_matrix_kernel<%s, %s>" % ("double" if rb == 8 else "float", kernel),
+                                          "note": "KernelMatrix %d x %d of the same micro-kernel: %d bytes written per pair, no reads to speak of; the peak is a read+write copy figure, a write-only stream can exceed it" % (nk, nk, k0 * k1 * rb)}
+        del d_M
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(res_ms) / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.real, "data": "synthetic", "config": config, "clocks": clocks,

@@ -626,8 +626,14 @@ int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, in
 // ---------------------------------------------------------------------------------------------
 // KernelMatrix
 // ---------------------------------------------------------------------------------------------
+// CTAs per SM a large matrix is cut into, for K1 > 1 and K1 == 1 kernels (tuning builds: tools/ab_build.sh;
+// profiles/r2l_kmat_grid_ab.md: the K1 == 1 kernels want fewer, longer CTAs -- more rows per target load -- FP32 odd
+// pitches +15 %, nothing lost elsewhere; K1 > 1 is flat within 3 % between 32 and 128)
 #ifndef SCTL_TUNE_KMAT_CTAS_PER_SM
-#define SCTL_TUNE_KMAT_CTAS_PER_SM 64  // CTAs per SM a large matrix is cut into (tuning builds: tools/ab_build.sh)
+#define SCTL_TUNE_KMAT_CTAS_PER_SM 64
+#endif
+#ifndef SCTL_TUNE_KMAT_CTAS_PER_SM_K1
+#define SCTL_TUNE_KMAT_CTAS_PER_SM_K1 32
 #endif
 template <class Real, int KID, bool DIRECT>
 int kmat_launch(int rsq, dim3 grid, int64_t Ns, int64_t Nt, int64_t rows_per_cta, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
@@ -644,13 +650,14 @@ int kmat_launch(int rsq, dim3 grid, int64_t Ns, int64_t Nt, int64_t rows_per_cta
 template <class Real, int KID>
 int kmat_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
   constexpr int T = KmatShape<Real, KID, false>::T, V = KmatShape<Real, KID, false>::V;  // the same for both paths
-  // A CTA keeps its KMAT_BT * T targets in registers and walks a contiguous range of source rows.  Enough CTAs for four
-  // full waves of the machine (16 CTAs of 128 threads per SM) when the matrix is that large, so that the last wave is
-  // short against the whole; never fewer CTAs than one per (target block, row) allows -- small blocks (hundreds x
+  // A CTA keeps its KMAT_BT * T targets in registers and walks a contiguous range of source rows.  Enough CTAs for several
+  // waves of the machine (8 - 12 CTAs of 128 threads are resident per SM) when the matrix is that large, so that the last
+  // wave is short against the whole; never fewer CTAs than one per (target block, row) allows -- small blocks (hundreds x
   // hundreds, boundary_integral.txx:1191-1211) are latency-bound and want every row on its own CTA.
   const int64_t n_tb = (Nt + KMAT_BT * T - 1) / (KMAT_BT * T);
   if (n_tb > 2147483647LL) return fail("too many target blocks");
-  const int64_t want_y = std::max<int64_t>(1, ((int64_t)g.dev[dev].sms * SCTL_TUNE_KMAT_CTAS_PER_SM + n_tb - 1) / n_tb);
+  constexpr int per_sm = KerTraits<KID>::K1 == 1 ? SCTL_TUNE_KMAT_CTAS_PER_SM_K1 : SCTL_TUNE_KMAT_CTAS_PER_SM;
+  const int64_t want_y = std::max<int64_t>(1, ((int64_t)g.dev[dev].sms * per_sm + n_tb - 1) / n_tb);
   const int64_t gy0 = std::min<int64_t>({Ns, want_y, 65535});
   const int64_t rows_per_cta = (Ns + gy0 - 1) / gy0;
   dim3 grid((unsigned)n_tb, (unsigned)((Ns + rows_per_cta - 1) / rows_per_cta));

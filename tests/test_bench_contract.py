@@ -39,6 +39,9 @@ def test_our_arm_line_small():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
     assert d["gpu_launches"] >= 2 * d["steps"]
     assert d["parity"]["max_abs_err_over_vinf"] <= 1e-12
+    km = r["kernel_matrix_view"]  # the path's HBM-bound kernel in the contract's hbm form
+    assert km["bound"] == "hbm" and km["unit"] == "GB/s" and {"achieved", "peak", "frac", "traffic"} <= set(km)
+    assert km["algorithmic_bytes_per_launch"] == 8192 * 3 * 8192 * 3 * 8 and 0.5 < km["frac"] < 1.3
     assert d["cpu_baseline"]["value"] > 0 and d["value"] > d["cpu_baseline"]["value"]
 
 
