@@ -148,7 +148,8 @@ def test_sass_evidence_of_the_b200_design(sbm):
     """cuobjdump of the shipped library: the shared-memory kernels stream sources with TMA bulk copies (UBLKCP) behind
     mbarriers (SYNCS), seed the reciprocal square root with MUFU.RSQ64H, and the constant-bank kernels feed FP64
     instructions with uniform-register operands loaded by LDCU (no vector LDC of the source records), and the FP32 pair loops
-    use the packed FP32 instructions with broadcast scalar operands."""
+    use the packed FP32 instructions with broadcast scalar operands; the KernelMatrix kernels store 16-byte vectors and keep
+    CTA barriers out of their row loop."""
     import shutil
     if not shutil.which("cuobjdump"):
         pytest.skip("cuobjdump not available")
@@ -177,6 +178,16 @@ def test_sass_evidence_of_the_b200_design(sbm):
             assert len(re.findall(r"F(FMA|MUL|ADD)2 [^;]*UR\d+\.F32", body)) >= 10, n
         if re.search(r"eval_pairs_kernelIfLi\d+ELi4E", n):  # T = 4 (main / wide); the few-target variant has T = 1
             assert len(re.findall(r"F(FMA|MUL|ADD)2 [^;]* -?R\d+\.F32", body)) >= 10, n
+    # KernelMatrix (csrc/kmat_kernel.cuh): every instantiation writes M with 16-byte vector stores, the staged ones move
+    # their stage with 16-byte shared-memory loads, and the only CTA barriers are the two around a source tile (one BAR.SYNC
+    # site per __syncthreads() call: two in the kernel, none added by the row loop)
+    kmat = {n: b for n, b in funcs.items() if "kernel_matrix_kernel" in n}
+    assert len(kmat) == 16 * 5 + 2 * 5  # 16 kernels x (3 FP64 + 2 FP32 digits classes) staged, + the direct forms of the two K1 == 1 kernels
+    for n, body in kmat.items():
+        assert "STG.E.128" in body, n
+        assert len(re.findall(r"BAR\.SYNC", body)) <= 2, n
+        if n.endswith("Lb0EEEvlllPKT_S3_S3_PS1_lS1_S1_"):  # staged
+            assert "LDS.128" in body and "WARPSYNC" in body, n
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", sbm.LIB_PATH], capture_output=True, text=True).stdout
 
 
