@@ -102,7 +102,10 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
 
 /* ---- the hot path: device pointers on the current device, enqueued on `stream` -------------- */
 /* (cudaStream_t passed as void*; NULL = the legacy default stream.)  Asynchronous: returns after enqueueing.
- * Pointers need no particular alignment.  Scratch comes from the stream-ordered pool (cudaMallocAsync). */
+ * Pointers need no particular alignment (beyond that of Real).  Scratch comes from the stream-ordered pool (cudaMallocAsync).
+ * KernelMatrix writes M with 16-byte vector stores whatever d_M and ldM are (rows that do not start on a 16-byte boundary
+ * get a scalar head and tail per warp); the single-component kernels (K1 == 1: Laplace3D_FxU / DxU) are fastest when d_M
+ * is 16-byte aligned and ldM is a multiple of 16 / real_bytes, which lets them store straight from registers. */
 
 int sctl_cuda_eval_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
                           const void* d_r_src, const void* d_n_src, const void* d_v_src, const void* d_r_trg, void* d_v_trg,
