@@ -4,9 +4,10 @@
 // the HBM write stream:
 //   * a CTA owns BT*T consecutive targets (register-resident, T per thread) of a contiguous range of source rows, so
 //     every matrix row it touches is one contiguous segment of BT*T*K1 Reals;
-//   * every global store is a 16-byte vector.  DIRECT (K1 == 1, M and the row pitch 16-byte aligned; chosen by the
-//     host): a thread's T = 16/sizeof(Real) consecutive targets are one vector, stored straight from registers (a warp
-//     writes 512 contiguous bytes per instruction).  Otherwise the K0 x (T*K1) values of a thread are staged through
+//   * every global store is a 16-byte vector.  K1 == 1: a thread's T = 16/sizeof(Real) consecutive targets are one
+//     vector, stored straight from registers (a warp writes 512 contiguous bytes per instruction); where rows do not all
+//     start on a 16-byte boundary (odd ldM, matrix views: KMAT_SHIFTED) every lane completes the aligned vector inside
+//     its columns with the first values of the next lane (one __shfl_down per value).  K1 > 1: the K0 x (T*K1) values of a thread are staged through
 //     shared memory, WARP by warp: a warp owns the 32*T*K1 contiguous columns of its lanes' targets, stages them in its
 //     own slice of shared memory and writes them out itself as aligned vectors, scalar elements only before the first
 //     and after the last 16-byte boundary of its segment -- rows need not be 16-byte aligned (odd ldM, matrix views),
@@ -34,23 +35,27 @@ template <> struct KmatVec<float> { using type = float4; };
 
 // Targets per thread: K1 == 1 -> one 16-byte vector of consecutive targets; K1 > 1 -> 8 bytes' worth of targets (the
 // staging buffer holds R * K0 * BT * T * K1 Reals: 27 KB for the K0 x K1 = 3 x 9 kernels in either precision).
-// Rows per round R: the source rows a thread computes before it stores.  DIRECT: 2 (independent pairs in flight).  Staged:
-// the cheap K1 == 1 kernels (13..19 instructions per pair) take 4 rows per round so that the round's address
-// arithmetic and its two __syncwarp() are spread over more pairs; K1 > 1 kernels do enough work per row.
+// Rows per round R: the source rows a thread computes before it stores.  DIRECT: 2 (independent pairs in flight).  Staged
+// (K1 > 1): 1, the kernels do enough work per row.
+// How a thread's values reach M.  KMAT_STAGED: K1 > 1.  K1 == 1: KMAT_DIRECT when every row starts on a 16-byte boundary (M
+// and the row pitch aligned; chosen by the host), KMAT_SHIFTED otherwise.
+enum : int { KMAT_STAGED = 0, KMAT_DIRECT = 1, KMAT_SHIFTED = 2 };
+
 template <class Real, int KID, bool DIRECT> struct KmatShape {
   static constexpr int V = 16 / (int)sizeof(Real);
   static constexpr int T = KerTraits<KID>::K1 == 1 ? V : 8 / (int)sizeof(Real);
-  static constexpr int R = DIRECT ? 2 : (KerTraits<KID>::K1 == 1 ? 4 : 1);
+  static constexpr int R = DIRECT ? 2 : 1;
 };
 
-template <class Real, int KID, int RSQ, bool DIRECT>
+template <class Real, int KID, int RSQ, int MODE>
 __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int64_t Nt, int64_t rows_per_cta, const Real* __restrict__ r_src, const Real* __restrict__ n_src,
                                                               const Real* __restrict__ r_trg, Real* __restrict__ M, int64_t ldM, Real scale, Real mu) {
   constexpr int K0 = KerTraits<KID>::K0, K1 = KerTraits<KID>::K1, ND = KerTraits<KID>::ND;
+  constexpr bool DIRECT = MODE != KMAT_STAGED;
   using Shape = KmatShape<Real, KID, DIRECT>;
   constexpr int BT = KMAT_BT, SB = KMAT_SRC_TILE, V = Shape::V, T = Shape::T, R = Shape::R;
   using Vec = typename KmatVec<Real>::type;
-  static_assert(!DIRECT || (K1 == 1 && T == V), "the direct path stores one vector of consecutive targets per row");
+  static_assert(DIRECT == (K1 == 1) && (!DIRECT || T == V), "K1 == 1: one vector of consecutive targets per row, straight from registers; K1 > 1: staged");
   static_assert(SB % R == 0, "a source tile is a whole number of rounds");
   constexpr int WW = 32 * T * K1;  // columns of a warp's part of the segment
   __shared__ Real xs_s[SB][3];
@@ -68,8 +73,9 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
   const int64_t c_warp = t_blk * K1 + (int64_t)warp * WW;  // first column of this warp's part
   const int64_t left = Nt * K1 - c_warp;
   const int n_col = (int)(left < 0 ? 0 : (left < WW ? left : WW));  // valid columns of this warp's part
-  // staged path: alignment of this warp's part.  a0 = elements between the last 16-byte boundary and the part's first
-  // column in matrix row 0, lmod = ldM mod V; `simple`: all rows of the part aligned and the part full
+  // alignment of this warp's part (and, K1 == 1, of every thread's first column).  a0 = elements between the last 16-byte
+  // boundary and the part's first column in matrix row 0, lmod = ldM mod V; `simple`: all rows of the part aligned and the
+  // part full
   constexpr int NV = WW / V;  // vectors per full part
   const int a0 = (int)(((uintptr_t)(M + c_warp) / sizeof(Real)) & (V - 1));
   const int lmod = (int)(ldM & (V - 1));
@@ -112,20 +118,59 @@ __global__ void __launch_bounds__(KMAT_BT) kernel_matrix_kernel(int64_t Ns, int6
       const int n_rows = ((nsb - si0) < R ? (nsb - si0) : R) * K0;  // matrix rows of this round
       const int64_t row0 = (tile + si0) * K0;
       if constexpr (DIRECT) {
-        // T == V consecutive targets of a row: one vector per (thread, row) straight from registers
+        // K1 == 1: a thread's T == V consecutive targets of a row.  Every thread's first column is a multiple of V past
+        // the CTA's first, so all of them sit `pad` elements past a 16-byte boundary in this row (pad depends on the row
+        // only).  pad == 0: the thread's values are one aligned vector.  Otherwise the aligned vector that starts inside
+        // the thread's columns is its last pad values followed by the first mis = V - pad values of the next lane
+        // (__shfl_down): lane i stores that vector, lane 0 also stores its own first mis values one by one and lane 31 its
+        // last pad values (the vector between two warps is written from both sides).
 #pragma unroll
         for (int rr = 0; rr < R * K0; rr++) {
           if (rr < n_rows) {
             Real* p = M + (row0 + rr) * ldM + t0;
-            if (t0 + T <= Nt) {
-              Real v[V];
+            const int pad = MODE == KMAT_DIRECT ? 0 : (a0 + ((int)(row0 + rr) & (V - 1)) * lmod) & (V - 1);
+            Real own[V];
 #pragma unroll
-              for (int j = 0; j < V; j++) v[j] = u[rr / K0][j][rr % K0];
-              *reinterpret_cast<Vec*>(p) = *reinterpret_cast<const Vec*>(v);
+            for (int j = 0; j < V; j++) own[j] = u[rr / K0][j][rr % K0];
+            if (MODE == KMAT_DIRECT || pad == 0) {
+              if (t0 + T <= Nt) {
+                *reinterpret_cast<Vec*>(p) = *reinterpret_cast<const Vec*>(own);
+              } else {
+#pragma unroll
+                for (int j = 0; j < T; j++)
+                  if (t0 + j < Nt) p[j] = own[j];
+              }
             } else {
+              const int mis = V - pad;
+              Real nb[V - 1];
 #pragma unroll
-              for (int j = 0; j < T; j++)
-                if (t0 + j < Nt) p[j] = u[rr / K0][j][rr % K0];
+              for (int j = 0; j < V - 1; j++) nb[j] = __shfl_down_sync(0xffffffffu, own[j], 1);
+              Real vec[V];
+#pragma unroll
+              for (int m = 1; m < V; m++)
+                if (mis == m) {
+#pragma unroll
+                  for (int e = 0; e < V; e++) vec[e] = (e < V - m) ? own[m + e] : nb[e - (V - m)];
+                }
+              const int64_t c = t0 + mis;  // first column of the vector
+              if (lane == 0) {
+#pragma unroll
+                for (int j = 0; j < V - 1; j++)
+                  if (j < mis && t0 + j < Nt) p[j] = own[j];
+              }
+              if (lane < 31) {
+                if (c + V <= Nt) {
+                  *reinterpret_cast<Vec*>(p + mis) = *reinterpret_cast<const Vec*>(vec);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < V; e++)
+                    if (c + e < Nt) p[mis + e] = vec[e];
+                }
+              } else {
+#pragma unroll
+                for (int e = 0; e < V - 1; e++)
+                  if (e < pad && c + e < Nt) p[mis + e] = vec[e];
+              }
             }
           }
         }

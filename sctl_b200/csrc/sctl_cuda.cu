@@ -635,13 +635,13 @@ int eval_device_any(int dev, int kid, int real_bytes, int digits, int64_t Ns, in
 #ifndef SCTL_TUNE_KMAT_CTAS_PER_SM_K1
 #define SCTL_TUNE_KMAT_CTAS_PER_SM_K1 32
 #endif
-template <class Real, int KID, bool DIRECT>
+template <class Real, int KID, int MODE>
 int kmat_launch(int rsq, dim3 grid, int64_t Ns, int64_t Nt, int64_t rows_per_cta, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
   const Real scale = scale_factor<Real>(KID);
   switch (rsq) {
-    case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, DIRECT><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
-    case RSQ_NEWTON: kernel_matrix_kernel<Real, KID, RSQ_NEWTON, DIRECT><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
-    default: kernel_matrix_kernel<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON), DIRECT><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+    case RSQ_SEED: kernel_matrix_kernel<Real, KID, RSQ_SEED, MODE><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+    case RSQ_NEWTON: kernel_matrix_kernel<Real, KID, RSQ_NEWTON, MODE><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
+    default: kernel_matrix_kernel<Real, KID, (sizeof(Real) == 8 ? RSQ_CUBIC : RSQ_NEWTON), MODE><<<grid, KMAT_BT, 0, stream>>>(Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, scale, ctx0); break;
   }
   CU_TRY(cudaGetLastError());
   return 0;
@@ -649,7 +649,7 @@ int kmat_launch(int rsq, dim3 grid, int64_t Ns, int64_t Nt, int64_t rows_per_cta
 
 template <class Real, int KID>
 int kmat_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src, const Real* n_src, const Real* r_trg, Real* M, int64_t ldM, Real ctx0, cudaStream_t stream) {
-  constexpr int T = KmatShape<Real, KID, false>::T, V = KmatShape<Real, KID, false>::V;  // the same for both paths
+  constexpr int T = KmatShape<Real, KID, false>::T;  // the same for both paths
   // A CTA keeps its KMAT_BT * T targets in registers and walks a contiguous range of source rows.  Enough CTAs for several
   // waves of the machine (8 - 12 CTAs of 128 threads are resident per SM) when the matrix is that large, so that the last
   // wave is short against the whole; never fewer CTAs than one per (target block, row) allows -- small blocks (hundreds x
@@ -663,10 +663,13 @@ int kmat_device_k(int dev, int digits, int64_t Ns, int64_t Nt, const Real* r_src
   dim3 grid((unsigned)n_tb, (unsigned)((Ns + rows_per_cta - 1) / rows_per_cta));
   const int rsq = rsq_mode_for_digits<Real>(digits);
   if constexpr (KerTraits<KID>::K1 == 1) {
-    // rows 16-byte aligned at every thread's first column: vectors go straight from registers to M
-    if ((uintptr_t)M % 16 == 0 && ldM % V == 0) return kmat_launch<Real, KID, true>(rsq, grid, Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+    // vectors go straight from registers to M; rows that do not all start on a 16-byte boundary take the lane-shifted form
+    constexpr int V = KmatShape<Real, KID, true>::V;
+    if ((uintptr_t)M % 16 == 0 && ldM % V == 0) return kmat_launch<Real, KID, KMAT_DIRECT>(rsq, grid, Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+    return kmat_launch<Real, KID, KMAT_SHIFTED>(rsq, grid, Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, ctx0, stream);
+  } else {
+    return kmat_launch<Real, KID, KMAT_STAGED>(rsq, grid, Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, ctx0, stream);  // warp-private stage
   }
-  return kmat_launch<Real, KID, false>(rsq, grid, Ns, Nt, rows_per_cta, r_src, n_src, r_trg, M, ldM, ctx0, stream);
 }
 
 template <class Real>

@@ -182,12 +182,16 @@ def test_sass_evidence_of_the_b200_design(sbm):
     # their stage with 16-byte shared-memory loads, and the only CTA barriers are the two around a source tile (one BAR.SYNC
     # site per __syncthreads() call: two in the kernel, none added by the row loop)
     kmat = {n: b for n, b in funcs.items() if "kernel_matrix_kernel" in n}
-    assert len(kmat) == 16 * 5 + 2 * 5  # 16 kernels x (3 FP64 + 2 FP32 digits classes) staged, + the direct forms of the two K1 == 1 kernels
+    # 14 K1 > 1 kernels x (3 FP64 + 2 FP32 digits classes) staged; the two K1 == 1 kernels in the direct and the lane-shifted form
+    assert len(kmat) == 14 * 5 + 2 * 5 * 2
     for n, body in kmat.items():
+        mode = int(re.search(r"kernel_matrix_kernelI[df]Li\d+ELi\dELi(\d)EEE", n).group(1))  # KMAT_STAGED / _DIRECT / _SHIFTED
         assert "STG.E.128" in body, n
         assert len(re.findall(r"BAR\.SYNC", body)) <= 2, n
-        if n.endswith("Lb0EEEvlllPKT_S3_S3_PS1_lS1_S1_"):  # staged
+        if mode == 0:
             assert "LDS.128" in body and "WARPSYNC" in body, n
+        if mode == 2:
+            assert "SHFL.DOWN" in body, n
     assert "sm_100a" in subprocess.run(["cuobjdump", "-lelf", sbm.LIB_PATH], capture_output=True, text=True).stdout
 
 
