@@ -104,8 +104,8 @@ int sctl_cuda_kernel_matrix(int kernel_id, int real_bytes, int digits, int64_t N
 /* (cudaStream_t passed as void*; NULL = the legacy default stream.)  Asynchronous: returns after enqueueing.
  * Pointers need no particular alignment (beyond that of Real).  Scratch comes from the stream-ordered pool (cudaMallocAsync).
  * KernelMatrix writes M with 16-byte vector stores whatever d_M and ldM are (rows that do not start on a 16-byte boundary
- * get a scalar head and tail per warp); the single-component kernels (K1 == 1: Laplace3D_FxU / DxU) are fastest when d_M
- * is 16-byte aligned and ldM is a multiple of 16 / real_bytes, which lets them store straight from registers. */
+ * get a few scalar elements where warps meet); it is fastest when d_M is 16-byte aligned and ldM is a multiple of
+ * 16 / real_bytes: an odd row pitch makes every warp store straddle one more 32-byte sector (70 - 90 % of the aligned rate). */
 
 int sctl_cuda_eval_device(int kernel_id, int real_bytes, int digits, int64_t Ns, int64_t Nt,
                           const void* d_r_src, const void* d_n_src, const void* d_v_src, const void* d_r_trg, void* d_v_trg,

@@ -7,13 +7,13 @@
 //   * every global store is a 16-byte vector.  K1 == 1: a thread's T = 16/sizeof(Real) consecutive targets are one
 //     vector, stored straight from registers (a warp writes 512 contiguous bytes per instruction); where rows do not all
 //     start on a 16-byte boundary (odd ldM, matrix views: KMAT_SHIFTED) every lane completes the aligned vector inside
-//     its columns with the first values of the next lane (one __shfl_down per value).  K1 > 1: the K0 x (T*K1) values of a thread are staged through
-//     shared memory, WARP by warp: a warp owns the 32*T*K1 contiguous columns of its lanes' targets, stages them in its
-//     own slice of shared memory and writes them out itself as aligned vectors, scalar elements only before the first
-//     and after the last 16-byte boundary of its segment -- rows need not be 16-byte aligned (odd ldM, matrix views),
-//     the staging index is shifted per row so that the shared-memory side of every vector is aligned too.  Only
-//     __syncwarp() orders the two phases: the row loop has no CTA barrier, so warps that are computing (the Helmholtz
-//     kernels spend ~70 FP64 instructions per pair) never wait for warps that are storing;
+//     its columns with the first values of the next lane (one __shfl_down per value).  K1 > 1: the K0 x (T*K1) values
+//     of a thread are staged through shared memory, WARP by warp: a warp owns the 32*T*K1 contiguous columns of its
+//     lanes' targets, stages them in its own slice of shared memory and writes them out itself as aligned vectors,
+//     scalar elements only before the first and after the last 16-byte boundary of its part -- rows need not be 16-byte
+//     aligned, the staging index is shifted per row so that the shared-memory side of every vector is aligned too.
+//     Only __syncwarp() orders the two phases: the row loop has no CTA barrier, so warps that are computing (the
+//     Helmholtz kernels spend ~70 FP64 instructions per pair) never wait for warps that are storing;
 //   * source coordinates (and normals) of a tile of rows are brought into shared memory by the whole CTA before the
 //     tile's rows are computed, so the row loop has no global load in it (round 1's kernel loaded them per row and
 //     spent its time on the long scoreboard: profiles/r1_ncu_kernel_matrix.md, 62 % / 40 % of the HBM copy bandwidth
@@ -33,14 +33,14 @@ template <class Real> struct KmatVec;
 template <> struct KmatVec<double> { using type = double2; };
 template <> struct KmatVec<float> { using type = float4; };
 
-// Targets per thread: K1 == 1 -> one 16-byte vector of consecutive targets; K1 > 1 -> 8 bytes' worth of targets (the
-// staging buffer holds R * K0 * BT * T * K1 Reals: 27 KB for the K0 x K1 = 3 x 9 kernels in either precision).
-// Rows per round R: the source rows a thread computes before it stores.  DIRECT: 2 (independent pairs in flight).  Staged
-// (K1 > 1): 1, the kernels do enough work per row.
 // How a thread's values reach M.  KMAT_STAGED: K1 > 1.  K1 == 1: KMAT_DIRECT when every row starts on a 16-byte boundary (M
 // and the row pitch aligned; chosen by the host), KMAT_SHIFTED otherwise.
 enum : int { KMAT_STAGED = 0, KMAT_DIRECT = 1, KMAT_SHIFTED = 2 };
 
+// Targets per thread T: K1 == 1 -> one 16-byte vector of consecutive targets; K1 > 1 -> 8 bytes' worth of targets (the
+// stage holds K0 * BT * T * K1 Reals: 27 KB for the K0 x K1 = 3 x 9 kernels in either precision).
+// Rows per round R: the source rows a thread computes before it stores.  Direct forms: 2 (independent pairs in flight);
+// staged: 1, the K1 > 1 kernels do enough work per row.
 template <class Real, int KID, bool DIRECT> struct KmatShape {
   static constexpr int V = 16 / (int)sizeof(Real);
   static constexpr int T = KerTraits<KID>::K1 == 1 ? V : 8 / (int)sizeof(Real);
